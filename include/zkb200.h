@@ -1,0 +1,107 @@
+/*
+ * zkb200.h -- C ABI of libzkb200.so, the B200 (sm_100a) Halo2/KZG proving backend.
+ *
+ * This is the boundary a fork-shaped `halo2_proofs` crate binds to: the reference swaps its
+ * prover backend at crate level (docker/testool/gpu/Dockerfile:7, cargo `paths` override of halo2_proofs), and the
+ * bodies of the upstream functions named below call these entry points instead of their rayon loops.  The
+ * reference-side call sites that reach them: circuit-benchmarks/src/super_circuit.rs:117-132 (create_proof),
+ * prover/src/common/prover/utils.rs:31 (gen_snark_shplonk), prover/src/common/prover/utils.rs:55 (keygen_pk2).
+ *
+ * Conventions (precedent: geth-utils/src/lib.rs:9-14 -- plain C types, explicit ownership):
+ *   - every function returns int32_t: 0 = ok, negative = error; zkb_last_error() gives a thread-local message.
+ *   - field elements / points are caller-owned buffers in halo2curves' in-memory layout (halo2curves 0.1.0 @ a495a7b):
+ *       Fr, Fq   : 4 x u64 little-endian limbs, Montgomery form (a * 2^256 mod p), fully reduced, 32 B
+ *       G1Affine : x || y, 64 B, identity = (0, 0)          G1 (projective) : x || y || z Jacobian, 96 B, identity z = 0
+ *     so Rust passes `slice.as_ptr()` with no conversion.
+ *   - `*_host` entry points take HOST pointers and include the H2D / D2H copies; `*_dev` take DEVICE pointers and a
+ *     CUDA stream (as void*, NULL = the context's stream) and never synchronise unless stated.
+ *   - opaque handles are created / destroyed explicitly; one proof at a time per context (the reference serialises
+ *     proving behind a Mutex<Prover>: prover/src/test/inner.rs:20-30).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with ZKB_ERR_CUDA.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ZKB_API __attribute__((visibility("default")))
+#else
+#define ZKB_API
+#endif
+
+#define ZKB_OK 0
+#define ZKB_ERR_CUDA (-1)    /* CUDA runtime failure or no device */
+#define ZKB_ERR_ARG (-2)     /* invalid argument */
+#define ZKB_ERR_ALLOC (-3)   /* device memory exhausted */
+#define ZKB_ERR_STATE (-4)   /* call sequence violated */
+
+typedef struct zkb_ctx zkb_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+/* Create a context on CUDA device `device` (one context per GPU / per process rank). */
+ZKB_API int32_t zkb_init(int32_t device, zkb_ctx **out);
+ZKB_API int32_t zkb_destroy(zkb_ctx *ctx);
+ZKB_API const char *zkb_last_error(void);
+/* ABI version of this header: major << 16 | minor */
+ZKB_API uint32_t zkb_version(void);
+/* Number of kernel launches issued through this context so far (bench.py's `gpu_launches`). */
+ZKB_API uint64_t zkb_launch_count(const zkb_ctx *ctx);
+ZKB_API int32_t zkb_sync(zkb_ctx *ctx);
+/* Stream the context launches on (cudaStream_t as void*), for event timing by the caller. */
+ZKB_API void *zkb_stream(zkb_ctx *ctx);
+
+/* ---- device memory (thin wrappers so a non-CUDA host language can own device buffers) --------------------- */
+ZKB_API int32_t zkb_malloc(zkb_ctx *ctx, uint64_t bytes, void **dptr);
+ZKB_API int32_t zkb_free(zkb_ctx *ctx, void *dptr);
+ZKB_API int32_t zkb_h2d(zkb_ctx *ctx, void *dst_dev, const void *src_host, uint64_t bytes);
+ZKB_API int32_t zkb_d2h(zkb_ctx *ctx, void *dst_host, const void *src_dev, uint64_t bytes);
+
+/* ---- NTT over Fr ------------------------------------------------------------------------------------------
+ * Replaces halo2_proofs::arithmetic::best_fft(a: &mut [Fr], omega: Fr, log_n: u32)   (halo2_proofs 1.1.0 @ e5ddf67
+ * src/arithmetic.rs) : in place, natural order in and out, a'[k] = sum_j a[j] * omega^(j k).  omega must have
+ * order exactly 2^log_n.  If `scale` is non-NULL every output is additionally multiplied by *scale (Montgomery Fr) --
+ * this fuses EvaluationDomain::ifft's `ifft_divisor` (src/poly/domain.rs `lagrange_to_coeff`, `extended_to_coeff`).
+ * If `coset_zeta` != 0 the input coefficient i is first multiplied by ZETA^(i mod 3) (coset_zeta = 1) or
+ * ZETA^(-(i mod 3)) applied to the OUTPUT (coset_zeta = 2), fusing `distribute_powers_zeta` of coeff_to_extended /
+ * extended_to_coeff.                                                                                         */
+ZKB_API int32_t zkb_ntt_fr_host(zkb_ctx *ctx, uint64_t *data_host, uint32_t log_n, const uint64_t omega[4],
+                        const uint64_t *scale /* 4 limbs or NULL */, int32_t coset_zeta);
+ZKB_API int32_t zkb_ntt_fr_dev(zkb_ctx *ctx, uint64_t *data_dev, uint32_t log_n, const uint64_t omega[4],
+                       const uint64_t *scale /* HOST pointer, 4 limbs or NULL */, int32_t coset_zeta, void *stream);
+/* omega_k = Fr::ROOT_OF_UNITY^(2^(28-k)) and its inverse (EvaluationDomain::new); host-side helper. */
+ZKB_API int32_t zkb_fr_root_of_unity(uint32_t k, uint64_t omega[4], uint64_t omega_inv[4]);
+
+/* ---- MSM over G1 -------------------------------------------------------------------------------------------
+ * Replaces halo2_proofs::arithmetic::best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1, the body of
+ * ParamsKZG::commit / commit_lagrange (src/poly/kzg/commitment.rs).  out = sum_i coeffs[i] * bases[i].
+ * The result is returned normalised: out_affine (64 B) and, if non-NULL, out_jacobian (96 B, z = 1 or identity) and
+ * out_compressed (32 B, G1Affine::to_bytes: LE x with (y & 1) << 6 in byte 31; identity = zeros).               */
+ZKB_API int32_t zkb_msm_g1_host(zkb_ctx *ctx, const uint64_t *scalars_host, const uint64_t *bases_host, uint64_t n,
+                        uint64_t out_affine[8], uint64_t *out_jacobian, uint8_t *out_compressed);
+ZKB_API int32_t zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, const uint64_t *bases_dev, uint64_t n,
+                       uint64_t out_affine[8], uint64_t *out_jacobian, uint8_t *out_compressed, void *stream);
+/* Number of bucket additions + reduction additions the last MSM on this context performed (G1-adds metric). */
+ZKB_API uint64_t zkb_msm_last_adds(const zkb_ctx *ctx);
+
+/* out[i] = [scalars[i]] * base, affine outputs (device buffers).  Used for ParamsKZG::setup / unsafe_setup_with_s
+ * (g[i] = [s^i] G) and to synthesise distinct benchmark bases.                                                  */
+ZKB_API int32_t zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_affine_host[8], const uint64_t *scalars_dev,
+                                  uint64_t n, uint64_t *out_affine_dev, void *stream);
+
+/* ---- element-wise field kernels (device buffers); field: 0 = Fr, 1 = Fq ------------------------------------
+ * op: 0 add, 1 sub, 2 mul (binary);  unary op: 0 invert (0 -> 0), 1 canonical->Montgomery, 2 Montgomery->canonical,
+ * 3 square, 4 negate.  These back Polynomial +,-,* and the unit tests of the device arithmetic.                  */
+ZKB_API int32_t zkb_field_binop_dev(zkb_ctx *ctx, int32_t field, int32_t op, const uint64_t *a, const uint64_t *b,
+                            uint64_t *out, uint64_t n, void *stream);
+ZKB_API int32_t zkb_field_unop_dev(zkb_ctx *ctx, int32_t field, int32_t op, const uint64_t *a, uint64_t *out, uint64_t n,
+                           void *stream);
+/* Montgomery batch inversion (halo2 `BatchInvert` / batch_invert_assigned): out[i] = a[i]^-1, zeros stay zero. */
+ZKB_API int32_t zkb_fr_batch_invert_dev(zkb_ctx *ctx, const uint64_t *a, uint64_t *out, uint64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,333 @@
+// msm.cu -- multi-scalar multiplication over BN254 G1 (Pippenger bucket method) for sm_100a.
+//
+// Replaces halo2_proofs::arithmetic::best_multiexp (halo2_proofs 1.1.0 @ e5ddf67 src/arithmetic.rs), the body of
+// ParamsKZG::commit / commit_lagrange (src/poly/kzg/commitment.rs) -- every commitment of create_proof
+// (circuit-benchmarks/src/super_circuit.rs:117-132).  Same contract: sum_i coeffs[i] * bases[i]; the group element is
+// unique, so the normalised (affine / compressed) output is bit-identical to the CPU prover's.
+//
+// B200 design (NOT upstream's per-thread serial windows):
+//   1. scalars leave Montgomery form once and are recoded into signed c-bit digits (W = ceil(255/c) windows, buckets
+//      1..2^(c-1) per window) -- coalesced 32-byte loads, one thread per scalar;
+//   2. a counting sort (histogram -> scan -> scatter) groups point indices by (window, |digit|): 4 bytes per
+//      (point, window) pair, no 64-byte point ever moves;
+//   3. one thread per bucket accumulates its points with mixed XYZZ additions (8M + 2S), gathering bases by index
+//      (a base is two 32-byte sectors);
+//   4. each window's buckets are reduced by segmented running sums (all windows and segments in parallel), the
+//      segment partials are tree-reduced per window, and the W window sums are combined by Horner doubling.
+//   Work is dominated by n*W mixed additions = n*W*10 Fq multiplies: bound by the integer-multiply pipe.
+#include "common.cuh"
+#include "g1.cuh"
+#include <string.h>
+
+namespace zkb {
+
+struct MsmCfg {
+    uint32_t c;         // window bits
+    uint32_t windows;   // W
+    uint32_t half;      // 2^(c-1) buckets per window
+    uint32_t seg_log;   // log2 of buckets per reduction segment
+};
+
+static MsmCfg choose_cfg(uint64_t n) {
+    uint32_t lg = 0;
+    while ((1ull << (lg + 1)) <= n) ++lg;
+    int c = (int)lg - 4;
+    if (c < 3) c = 3;
+    if (c > 20) c = 20;
+    MsmCfg m;
+    m.c = (uint32_t)c;
+    m.windows = (255 + m.c - 1) / m.c;
+    m.half = 1u << (m.c - 1);
+    m.seg_log = m.c - 1 > 7 ? 7 : m.c - 1;
+    return m;
+}
+
+// signed-digit recoding of a canonical scalar (8 x u32), window w; carry chain recomputed from window 0
+__device__ __forceinline__ uint32_t raw_window(const uint32_t s[8], uint32_t bit, uint32_t c) {
+    const uint32_t limb = bit >> 5, off = bit & 31;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> off) & ((1u << c) - 1);
+}
+
+// mode 0: histogram; mode 1: scatter
+template <int MODE>
+__global__ void msm_digits_kernel(const Fr *__restrict__ scalars, uint64_t n, MsmCfg m, uint32_t *__restrict__ counts,
+                                  uint32_t *__restrict__ cursors, uint32_t *__restrict__ sorted) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr s = fp_to_canonical(fp_load(scalars + i));
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < m.windows; ++w) {
+        const uint32_t bit = w * m.c;
+        uint32_t d = (bit < 256 ? raw_window(s.l, bit, m.c) : 0) + carry;
+        uint32_t neg = 0;
+        if (d > m.half) { d = (1u << m.c) - d; neg = 1; carry = 1; }
+        else carry = 0;
+        if (d != 0) {
+            const uint32_t b = w * m.half + (d - 1);
+            if (MODE == 0) atomicAdd(&counts[b], 1u);
+            else {
+                const uint32_t pos = atomicAdd(&cursors[b], 1u);
+                sorted[pos] = (uint32_t)i | (neg << 31);
+            }
+        }
+    }
+}
+
+// ---- exclusive scan of u32 (three small kernels) -----------------------------------------------------------
+constexpr int SCAN_T = 512, SCAN_PER = 4, SCAN_BLK = SCAN_T * SCAN_PER;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total, uint32_t *sm /* SCAN_T/32 */) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sm[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = lane < (blockDim.x >> 5) ? sm[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        sm[lane] = t;
+    }
+    __syncthreads();
+    const uint32_t base = wid ? sm[wid - 1] : 0;
+    *total = sm[(blockDim.x >> 5) - 1];
+    return base + x - v;
+}
+
+__global__ void scan_blocks_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t *__restrict__ block_sums, uint64_t n) {
+    __shared__ uint32_t sm[32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLK + (uint64_t)threadIdx.x * SCAN_PER;
+    uint32_t v[SCAN_PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) { v[k] = base + k < n ? in[base + k] : 0; sum += v[k]; }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(sum, &total, sm);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void scan_sums_kernel(uint32_t *__restrict__ block_sums, uint32_t nblocks, uint32_t *__restrict__ grand_total) {
+    // single block; serial over chunks of SCAN_T
+    __shared__ uint32_t sm[32];
+    uint32_t running = 0;
+    for (uint32_t s = 0; s < nblocks; s += SCAN_T) {
+        const uint32_t idx = s + threadIdx.x;
+        const uint32_t v = idx < nblocks ? block_sums[idx] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, &total, sm);
+        if (idx < nblocks) block_sums[idx] = running + ex;
+        running += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && grand_total) *grand_total = running;
+}
+__global__ void scan_add_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ block_sums, uint64_t n) {
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLK + (uint64_t)threadIdx.x * SCAN_PER;
+    const uint32_t add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+// out[0..n) = exclusive scan of in, out[n] = total.  tmp: ceil(n / SCAN_BLK) u32
+static void exclusive_scan_u32(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *tmp, cudaStream_t st) {
+    const uint32_t nblocks = (uint32_t)((n + SCAN_BLK - 1) / SCAN_BLK);
+    scan_blocks_kernel<<<nblocks, SCAN_T, 0, st>>>(in, out, tmp, n);
+    scan_sums_kernel<<<1, SCAN_T, 0, st>>>(tmp, nblocks, out + n);
+    scan_add_kernel<<<nblocks, SCAN_T, 0, st>>>(out, tmp, n);
+    ctx->launches += 3;
+}
+
+// ---- bucket accumulation: one thread per bucket -------------------------------------------------------------
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__restrict__ bases, const uint32_t *__restrict__ offsets,
+                                                            const uint32_t *__restrict__ sorted, G1Xyzz *__restrict__ buckets,
+                                                            uint32_t nbuckets) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    const uint32_t beg = offsets[b], end = offsets[b + 1];
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t k = beg; k < end; ++k) {
+        const uint32_t e = sorted[k];
+        G1Affine p = g1_load_affine(bases + (e & 0x7fffffffu));
+        if (e >> 31) p = g1_neg(p);
+        g1_add_mixed(acc, p);
+    }
+    g1_store_xyzz(buckets + b, acc);
+}
+
+// ---- window reduction, stage 1: segment running sums ---------------------------------------------------------
+// thread (w, seg): buckets j in [seg*L, (seg+1)*L) of window w (bucket j has weight j+1)
+//   partial = sum_j (j + 1) * B_j = sum_j (j - seg*L + 1) * B_j + (seg*L) * sum_j B_j
+__global__ void __launch_bounds__(128) msm_segment_kernel(const G1Xyzz *__restrict__ buckets, G1Xyzz *__restrict__ partials, MsmCfg m) {
+    const uint32_t segs = m.half >> m.seg_log;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m.windows * segs) return;
+    const uint32_t w = t / segs, seg = t % segs;
+    const uint32_t L = 1u << m.seg_log;
+    const G1Xyzz *bk = buckets + (size_t)w * m.half + (size_t)seg * L;
+    G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity();
+    for (int j = (int)L - 1; j >= 0; --j) {
+        g1_add(running, g1_load_xyzz(bk + j));
+        g1_add(acc, running);
+    }
+    // acc += (seg * L) * running   (double-and-add, MSB first)
+    const uint32_t k = seg * L;
+    if (k) {
+        G1Xyzz r = G1Xyzz::identity();
+        for (int bit = 31 - __clz(k); bit >= 0; --bit) {
+            r = g1_dbl(r);
+            if ((k >> bit) & 1) g1_add(r, running);
+        }
+        g1_add(acc, r);
+    }
+    g1_store_xyzz(partials + t, acc);
+}
+
+// ---- window reduction, stage 2: tree-sum the segment partials of one window (one block per window) -----------
+__global__ void __launch_bounds__(256) msm_window_sum_kernel(const G1Xyzz *__restrict__ partials, G1Xyzz *__restrict__ window_sums, uint32_t segs) {
+    extern __shared__ uint4 sm4[];
+    G1Xyzz *sm = reinterpret_cast<G1Xyzz *>(sm4);
+    const uint32_t w = blockIdx.x;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t s = threadIdx.x; s < segs; s += blockDim.x) g1_add(acc, g1_load_xyzz(partials + (size_t)w * segs + s));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            G1Xyzz a = sm[threadIdx.x];
+            g1_add(a, sm[threadIdx.x + o]);
+            sm[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) g1_store_xyzz(window_sums + w, sm[0]);
+}
+
+// ---- fixed-base scalar multiplication: out[i] = [s_i] base (affine) ------------------------------------------
+__global__ void __launch_bounds__(128) fixed_base_mul_kernel(G1Affine base, const Fr *__restrict__ scalars, uint64_t n, G1Affine *__restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr s = fp_to_canonical(fp_load(scalars + i));
+    G1Xyzz acc = G1Xyzz::identity();
+    for (int bit = 253; bit >= 0; --bit) {
+        acc = g1_dbl(acc);
+        if ((s.l[bit >> 5] >> (bit & 31)) & 1) g1_add_mixed(acc, base);
+    }
+    g1_store_affine(out + i, g1_to_affine(acc));
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, uint64_t n, G1Affine *out_affine_host, cudaStream_t st) {
+    ZKB_ARG(n < (1ull << 31));
+    if (n == 0) {
+        memset(out_affine_host, 0, sizeof(G1Affine));
+        ctx->msm_last_adds = 0;
+        return ZKB_OK;
+    }
+    const MsmCfg m = choose_cfg(n);
+    const uint32_t nbuckets = m.windows * m.half;
+    const uint32_t segs = m.half >> m.seg_log;
+    const uint64_t pairs = n * m.windows;
+    ZKB_ARG(pairs < (1ull << 32));
+
+    // scratch layout A: counts | offsets(+1) | cursors | scan tmp ; B: sorted ; C: buckets | partials | window sums
+    const size_t cnt_bytes = align_up((size_t)(nbuckets + 1) * 4, 256);
+    const size_t tmp_bytes = align_up(((size_t)nbuckets / SCAN_BLK + 2) * 4, 256);
+    uint8_t *A = nullptr, *B = nullptr, *C = nullptr;
+    ZKB_TRY(scratch_get(ctx, SCR_MSM_A, 3 * cnt_bytes + tmp_bytes, (void **)&A));
+    ZKB_TRY(scratch_get(ctx, SCR_MSM_B, pairs * 4, (void **)&B));
+    const size_t bucket_bytes = (size_t)nbuckets * sizeof(G1Xyzz), part_bytes = (size_t)m.windows * segs * sizeof(G1Xyzz);
+    ZKB_TRY(scratch_get(ctx, SCR_MSM_C, bucket_bytes + part_bytes + m.windows * sizeof(G1Xyzz), (void **)&C));
+    uint32_t *counts = (uint32_t *)A, *offsets = (uint32_t *)(A + cnt_bytes), *cursors = (uint32_t *)(A + 2 * cnt_bytes);
+    uint32_t *scan_tmp = (uint32_t *)(A + 3 * cnt_bytes);
+    uint32_t *sorted = (uint32_t *)B;
+    G1Xyzz *buckets = (G1Xyzz *)C, *partials = (G1Xyzz *)(C + bucket_bytes), *wsums = (G1Xyzz *)(C + bucket_bytes + part_bytes);
+
+    ZKB_CUDA(cudaMemsetAsync(counts, 0, cnt_bytes, st));
+    const unsigned tb = 256, gb = (unsigned)((n + tb - 1) / tb);
+    msm_digits_kernel<0><<<gb, tb, 0, st>>>(scalars, n, m, counts, nullptr, nullptr);
+    exclusive_scan_u32(ctx, counts, offsets, nbuckets, scan_tmp, st);
+    ZKB_CUDA(cudaMemcpyAsync(cursors, offsets, (size_t)nbuckets * 4, cudaMemcpyDeviceToDevice, st));
+    msm_digits_kernel<1><<<gb, tb, 0, st>>>(scalars, n, m, nullptr, cursors, sorted);
+    msm_accumulate_kernel<<<(nbuckets + 127) / 128, 128, 0, st>>>(bases, offsets, sorted, buckets, nbuckets);
+    msm_segment_kernel<<<(m.windows * segs + 127) / 128, 128, 0, st>>>(buckets, partials, m);
+    uint32_t wt = 32;
+    while (wt < segs && wt < 256) wt <<= 1;
+    msm_window_sum_kernel<<<m.windows, wt, wt * sizeof(G1Xyzz), st>>>(partials, wsums, segs);
+    ctx->launches += 5;
+    ZKB_CUDA(cudaGetLastError());
+
+    std::vector<G1Xyzz> h(m.windows);
+    uint32_t total_pairs = 0;
+    ZKB_CUDA(cudaMemcpyAsync(h.data(), wsums, m.windows * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaMemcpyAsync(&total_pairs, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaStreamSynchronize(st));
+    // Horner over windows on the host (W * c doublings + W additions of single points)
+    G1Xyzz acc = h[m.windows - 1];
+    for (int w = (int)m.windows - 2; w >= 0; --w) {
+        for (uint32_t k = 0; k < m.c; ++k) acc = g1_dbl(acc);
+        g1_add(acc, h[w]);
+    }
+    *out_affine_host = g1_to_affine(acc);
+    ctx->msm_last_adds = (uint64_t)total_pairs + 2ull * nbuckets + (uint64_t)m.windows * segs;
+    return ZKB_OK;
+}
+
+}  // namespace zkb
+using namespace zkb;
+
+static void emit_outputs(const G1Affine &r, uint64_t out_affine[8], uint64_t *out_jacobian, uint8_t *out_compressed) {
+    memcpy(out_affine, &r, 64);
+    if (out_jacobian) {
+        memcpy(out_jacobian, &r, 64);
+        Fq z = r.is_identity() ? Fq::zero() : Fq::one();  // identity = (0, 0, 0), any z = 0 point is the identity
+        memcpy(out_jacobian + 8, &z, 32);
+    }
+    if (out_compressed) g1_compress(r, out_compressed);
+}
+
+extern "C" int32_t zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, const uint64_t *bases_dev, uint64_t n, uint64_t out_affine[8],
+                                  uint64_t *out_jacobian, uint8_t *out_compressed, void *stream) {
+    ZKB_ARG(ctx && out_affine && (n == 0 || (scalars_dev && bases_dev)));
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+    G1Affine r;
+    ZKB_TRY(msm_g1_device(ctx, (const Fr *)scalars_dev, (const G1Affine *)bases_dev, n, &r, pick_stream(ctx, stream)));
+    emit_outputs(r, out_affine, out_jacobian, out_compressed);
+    return ZKB_OK;
+}
+
+extern "C" int32_t zkb_msm_g1_host(zkb_ctx *ctx, const uint64_t *scalars_host, const uint64_t *bases_host, uint64_t n, uint64_t out_affine[8],
+                                   uint64_t *out_jacobian, uint8_t *out_compressed) {
+    ZKB_ARG(ctx && out_affine && (n == 0 || (scalars_host && bases_host)));
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+    void *ds = nullptr, *db = nullptr;
+    if (n) {
+        ZKB_TRY(scratch_get(ctx, SCR_HOSTIO_A, n * 32, &ds));
+        ZKB_TRY(scratch_get(ctx, SCR_HOSTIO_B, n * 64, &db));
+        ZKB_CUDA(cudaMemcpyAsync(ds, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ZKB_CUDA(cudaMemcpyAsync(db, bases_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return zkb_msm_g1_dev(ctx, (const uint64_t *)ds, (const uint64_t *)db, n, out_affine, out_jacobian, out_compressed, ctx->stream);
+}
+
+extern "C" int32_t zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_affine_host[8], const uint64_t *scalars_dev, uint64_t n,
+                                             uint64_t *out_affine_dev, void *stream) {
+    ZKB_ARG(ctx && base_affine_host && scalars_dev && out_affine_dev);
+    if (n == 0) return ZKB_OK;
+    G1Affine base;
+    memcpy(&base, base_affine_host, 64);
+    fixed_base_mul_kernel<<<(unsigned)((n + 127) / 128), 128, 0, pick_stream(ctx, stream)>>>(base, (const Fr *)scalars_dev, n, (G1Affine *)out_affine_dev);
+    ctx->launches++;
+    ZKB_CUDA(cudaGetLastError());
+    return ZKB_OK;
+}

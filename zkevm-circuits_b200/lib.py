@@ -1,0 +1,111 @@
+"""ctypes binding of libzkb200.so (the C ABI declared in include/zkb200.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is present, every compute entry
+point raises ZkbError.  Build with `python -c "import __graft_entry__ as g; g.build()"` or `make -C zkevm-circuits_b200/csrc`.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libzkb200.so")
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_vp = ctypes.c_void_p
+
+
+class ZkbError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); must list every symbol include/zkb200.h declares (checked by tests/test_abi.py)
+SIGNATURES = {
+    "zkb_init": (ctypes.c_int32, [ctypes.c_int32, ctypes.POINTER(_vp)]),
+    "zkb_destroy": (ctypes.c_int32, [_vp]),
+    "zkb_last_error": (ctypes.c_char_p, []),
+    "zkb_version": (ctypes.c_uint32, []),
+    "zkb_launch_count": (ctypes.c_uint64, [_vp]),
+    "zkb_sync": (ctypes.c_int32, [_vp]),
+    "zkb_stream": (_vp, [_vp]),
+    "zkb_malloc": (ctypes.c_int32, [_vp, ctypes.c_uint64, ctypes.POINTER(_vp)]),
+    "zkb_free": (ctypes.c_int32, [_vp, _vp]),
+    "zkb_h2d": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64]),
+    "zkb_d2h": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64]),
+    "zkb_ntt_fr_host": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint32, _vp, _vp, ctypes.c_int32]),
+    "zkb_ntt_fr_dev": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint32, _vp, _vp, ctypes.c_int32, _vp]),
+    "zkb_fr_root_of_unity": (ctypes.c_int32, [ctypes.c_uint32, _vp, _vp]),
+    "zkb_msm_g1_host": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp]),
+    "zkb_msm_g1_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp]),
+    "zkb_msm_last_adds": (ctypes.c_uint64, [_vp]),
+    "zkb_g1_fixed_base_mul_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
+    "zkb_field_binop_dev": (ctypes.c_int32, [_vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_uint64, _vp]),
+    "zkb_field_unop_dev": (ctypes.c_int32, [_vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, ctypes.c_uint64, _vp]),
+    "zkb_fr_batch_invert_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64, _vp]),
+}
+
+_lib = None
+
+
+def load_library():
+    """Load libzkb200.so and attach signatures.  Raises ZkbError when the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ZkbError(f"{LIB_PATH} is missing: build the CUDA extension first (__graft_entry__.build()); "
+                       "zkb200 has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load_library().zkb_last_error()
+        raise ZkbError(f"libzkb200 error {rc}: {msg.decode() if msg else ''}")
+
+
+class Context:
+    """One per GPU (per process rank).  Mirrors the process-global, mutex-guarded prover state the reference keeps
+    (prover/src/test/inner.rs:20-30)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _vp()
+        check(self.lib.zkb_init(int(device), ctypes.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if self.handle:
+            self.lib.zkb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self.lib.zkb_launch_count(self.handle))
+
+    def sync(self):
+        check(self.lib.zkb_sync(self.handle))
+
+
+_default = {}
+
+
+def default_context(device=None):
+    import torch
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]
