@@ -26,8 +26,11 @@ def _limbs_ptr(x):
 
 
 def _cur_stream():
+    """torch's current stream as a cudaStream_t.  torch reports the legacy default stream as 0, which the C ABI reads
+    as "use the context's own stream"; pass cudaStreamLegacy (0x1) instead so launches stay ordered with torch's work."""
     import torch
-    return _vp(torch.cuda.current_stream().cuda_stream)
+    s = torch.cuda.current_stream().cuda_stream
+    return _vp(s if s else 1)
 
 
 def root_of_unity(k):
