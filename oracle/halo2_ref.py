@@ -1,0 +1,807 @@
+"""CPU restatement of halo2_proofs' KZG/SHPLONK prover + verifier (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+
+Follows the published algorithm of halo2_proofs 1.1.0 = scroll-tech/halo2 branch v1.1 @ e5ddf67 (source NOT under
+/root/reference; restated):
+  plonk/prover.rs (create_proof flow and transcript order), plonk/circuit.rs (blinding_factors, degree),
+  poly/domain.rs (EvaluationDomain), plonk/permutation/{keygen,prover}.rs, plonk/mv_lookup/prover.rs (logUp),
+  plonk/vanishing/prover.rs, plonk/evaluation.rs (evaluate_h term order), poly/kzg/multiopen/shplonk/{prover,verifier}.rs
+  and shplonk.rs (construct_intermediate_sets), transcript/blake2b.rs.
+Facts pinned by the reference's own fixture aggregator/data/batch-task.json (tests/golden): proof layout
+[advice | m | z, phi, random | h pieces | evals | W, W'], evaluation order [advice, fixed, random, sigma, z(x), z(wx),
+phi(x), phi(wx), m(x)], query order, the logUp / permutation constraint formulas (Protocol.quotient.numerator), l_last = L_{-(bf+1)}.
+Whole-proof bytes are NOT pinned by any reference test (no golden proof of a circuit we can synthesise): parity unpinned
+beyond "this verifier (same equations as upstream's) accepts".
+
+Arithmetic: arrays go through oracle/libzkoracle.so (numpy uint64 (n,4) Montgomery limbs); scalars are Python ints.
+Blinding scalars and vk.transcript_repr are inputs (their derivation is Rust-specific: RNG draw order, Debug hash).
+"""
+import hashlib
+import numpy as np
+
+import pyref as P
+import oracle_lib
+
+R = P.R_MOD
+CONST, FIXED, ADVICE, INSTANCE, CHALLENGE, NEG, ADD, MUL, SCALED = range(9)
+
+
+# ------------------------------------------------------------------------------------------------ expressions
+class Expr:
+    """Expression DAG node (halo2 plonk::Expression without selectors: they are fixed columns by proving time)."""
+    __slots__ = ("op", "a", "b")
+
+    def __init__(self, op, a=None, b=None):
+        self.op, self.a, self.b = op, a, b
+
+    def __add__(self, o): return Expr(ADD, self, o)
+    def __mul__(self, o): return Expr(MUL, self, o)
+    def __neg__(self): return Expr(NEG, self)
+    def __sub__(self, o): return Expr(ADD, self, Expr(NEG, o))
+
+    def degree(self):
+        if self.op in (CONST, CHALLENGE): return 0
+        if self.op in (FIXED, ADVICE, INSTANCE): return 1
+        if self.op == NEG: return self.a.degree()
+        if self.op == ADD: return max(self.a.degree(), self.b.degree())
+        if self.op == MUL: return self.a.degree() + self.b.degree()
+        if self.op == SCALED: return self.a.degree()
+        raise ValueError
+
+
+def const(v): return Expr(CONST, v % R)
+def fixed(c, rot=0): return Expr(FIXED, c, rot)
+def advice(c, rot=0): return Expr(ADVICE, c, rot)
+def instance(c, rot=0): return Expr(INSTANCE, c, rot)
+def challenge(i): return Expr(CHALLENGE, i)
+def scaled(e, v): return Expr(SCALED, e, v % R)
+
+
+class Lookup:
+    """mv-lookup argument after chunk_lookups(): several input expression vectors against one table vector."""
+    def __init__(self, inputs, table):
+        self.inputs = inputs    # list of list of Expr (each inner list has len(table) entries)
+        self.table = table      # list of Expr
+
+    def required_degree(self):
+        ideg = sum(max(e.degree() for e in inp) for inp in self.inputs)
+        tdeg = max(max(e.degree() for e in self.table), 1)
+        return max(4, 2 + ideg + tdeg)
+
+
+class ConstraintSystem:
+    def __init__(self, k, num_fixed, num_advice, num_instance, advice_phase=None, challenge_phase=None):
+        self.k, self.n = k, 1 << k
+        self.num_fixed, self.num_advice, self.num_instance = num_fixed, num_advice, num_instance
+        self.advice_phase = advice_phase or [0] * num_advice
+        self.challenge_phase = challenge_phase or []
+        self.gates = []          # list of Expr, constraint-system order
+        self.lookups = []        # list of Lookup
+        self.perm_columns = []   # list of (type, index) with type in {FIXED, ADVICE, INSTANCE}
+        self.advice_queries, self.fixed_queries, self.instance_queries = [], [], []
+
+    # -- queries: order of first use, as halo2's ConstraintSystem::query_* records them
+    def _collect(self, e):
+        if e.op == ADVICE and (e.a, e.b) not in self.advice_queries: self.advice_queries.append((e.a, e.b))
+        elif e.op == FIXED and (e.a, e.b) not in self.fixed_queries: self.fixed_queries.append((e.a, e.b))
+        elif e.op == INSTANCE and (e.a, e.b) not in self.instance_queries: self.instance_queries.append((e.a, e.b))
+        elif e.op in (NEG, SCALED): self._collect(e.a)
+        elif e.op in (ADD, MUL): self._collect(e.a); self._collect(e.b)
+
+    def finalize(self):
+        for g in self.gates: self._collect(g)
+        for lk in self.lookups:
+            for inp in lk.inputs:
+                for e in inp: self._collect(e)
+            for e in lk.table: self._collect(e)
+        # enable_equality queries the column at rotation 0
+        for (t, i) in self.perm_columns:
+            q = {ADVICE: self.advice_queries, FIXED: self.fixed_queries, INSTANCE: self.instance_queries}[t]
+            if (i, 0) not in q: q.append((i, 0))
+        return self
+
+    def degree(self):
+        d = 3 if self.perm_columns else 1           # permutation::Argument::required_degree() = 3
+        for lk in self.lookups: d = max(d, lk.required_degree())
+        for g in self.gates: d = max(d, g.degree())
+        return max(d, 3)
+
+    def blinding_factors(self):
+        per_col = {}
+        for (c, _) in self.advice_queries: per_col[c] = per_col.get(c, 0) + 1
+        return max(3, max(per_col.values(), default=1)) + 2
+
+    def num_phases(self):
+        return max(self.advice_phase + self.challenge_phase + [0]) + 1
+
+
+# ------------------------------------------------------------------------------------------------ field arrays
+class FA:
+    """Thin array layer over the C oracle."""
+    def __init__(self):
+        self.o = oracle_lib.load()
+
+    def arr(self, ints):
+        c = np.array([P.limbs(v % R) for v in ints], dtype=np.uint64).reshape(-1, 4)
+        return self.o.fr_from_canonical(c)
+
+    def full(self, v, n): return np.repeat(self.arr([v]), n, axis=0)
+    def ints(self, a):
+        c = self.o.fr_to_canonical(np.ascontiguousarray(a))
+        return [P.from_limbs(r) for r in c]
+    def add(self, a, b): return self.o.fr_add(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    def sub(self, a, b): return self.o.fr_sub(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    def mul(self, a, b): return self.o.fr_mul(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    def inv(self, a): return self.o.fr_inv(np.ascontiguousarray(a))
+    def scal(self, a, v): return self.mul(a, self.full(v, a.shape[0]))
+    def addc(self, a, v): return self.add(a, self.full(v, a.shape[0]))
+    def neg(self, a): return self.sub(np.zeros_like(a), a)
+    def powers(self, base, n):
+        w = self.arr([base])[0]
+        return self.o.fr_powers(w, n)
+
+
+def rot(a, r, step=1):
+    """value at row (i + r*step) mod len."""
+    return np.roll(a, -r * step, axis=0)
+
+
+# ------------------------------------------------------------------------------------------------ domain
+class Domain:
+    """halo2_proofs poly/domain.rs EvaluationDomain::new(j = cs.degree(), k)."""
+    def __init__(self, k, cs_degree):
+        self.k, self.n = k, 1 << k
+        self.qdeg = cs_degree - 1
+        ek = k
+        while (1 << ek) < self.n * self.qdeg: ek += 1
+        self.extended_k, self.N = ek, 1 << ek
+        self.extended_omega = pow(P.FR_ROOT_OF_UNITY, 1 << (P.FR_S - ek), R)
+        self.omega = pow(self.extended_omega, 1 << (ek - k), R)
+        self.omega_inv = pow(self.omega, -1, R)
+        self.extended_omega_inv = pow(self.extended_omega, -1, R)
+        self.g_coset, self.g_coset_inv = P.FR_ZETA, pow(P.FR_ZETA, 2, R)
+        self.ifft_divisor = pow(self.n, -1, R)
+        self.extended_ifft_divisor = pow(self.N, -1, R)
+        self.E = self.N // self.n
+        self.t_evaluations = [(pow(P.FR_ZETA * pow(self.extended_omega, i, R) % R, self.n, R) - 1) % R for i in range(self.E)]
+
+    def rotate_omega(self, x, r):
+        return x * pow(self.omega, r, R) % R if r >= 0 else x * pow(self.omega_inv, -r, R) % R
+
+
+class Ref:
+    """Reference prover/verifier bound to one (cs, srs)."""
+    def __init__(self, cs, srs_s):
+        self.F = FA()
+        self.o = self.F.o
+        self.cs = cs
+        self.d = cs.degree()
+        self.dom = Domain(cs.k, self.d)
+        self.bf = cs.blinding_factors()
+        self.chunk = self.d - 2
+        self.s = srs_s % R
+        n = cs.n
+        # ParamsKZG::unsafe_setup_with_s: g[i] = [s^i] G ; g_lagrange[i] = [L_i(s)] G  (poly/kzg/commitment.rs)
+        G = self.o.g1_generator()
+        pw = self.o.fr_powers(self.F.arr([self.s])[0], n)
+        self.g = self.o.g1_fixed_base_mul(G, pw)
+        # L_i(s) = w^i (s^n - 1) / (n (s - w^i))
+        F = self.F
+        wi = F.powers(self.dom.omega, n)
+        den = F.scal(F.sub(F.full(self.s, n), wi), n)
+        num = F.scal(wi, (pow(self.s, n, R) - 1) % R)
+        self.g_lagrange = self.o.g1_fixed_base_mul(G, F.mul(num, F.inv(den)))
+
+    # ---- basis conversions
+    def w_arr(self, v): return self.F.arr([v])[0]
+
+    def lagrange_to_coeff(self, a):
+        out = self.o.best_fft(a, self.w_arr(self.dom.omega_inv), self.dom.k)
+        return self.F.scal(out, self.dom.ifft_divisor)
+
+    def coeff_to_extended(self, a):
+        F, dom = self.F, self.dom
+        n = a.shape[0]
+        zp = np.stack([self.w_arr(1), self.w_arr(dom.g_coset), self.w_arr(dom.g_coset_inv)])[np.arange(n) % 3]
+        b = np.zeros((dom.N, 4), dtype=np.uint64)
+        b[:n] = F.mul(a, zp)
+        return self.o.best_fft(b, self.w_arr(dom.extended_omega), dom.extended_k)
+
+    def extended_to_coeff(self, a):
+        F, dom = self.F, self.dom
+        out = F.scal(self.o.best_fft(a, self.w_arr(dom.extended_omega_inv), dom.extended_k), dom.extended_ifft_divisor)
+        zp = np.stack([self.w_arr(1), self.w_arr(dom.g_coset_inv), self.w_arr(dom.g_coset)])[np.arange(dom.N) % 3]
+        return F.mul(out, zp)[: dom.n * dom.qdeg]
+
+    def commit(self, coeffs):
+        return self.o.g1_to_affine(self.o.best_multiexp(np.ascontiguousarray(coeffs), self.g[: coeffs.shape[0]]))
+
+    def commit_lagrange(self, values):
+        return self.o.g1_to_affine(self.o.best_multiexp(np.ascontiguousarray(values), self.g_lagrange))
+
+    def eval_poly(self, coeffs, x):
+        acc = 0
+        for c in reversed(self.F.ints(coeffs)):
+            acc = (acc * x + c) % R
+        return acc
+
+    # ---- keygen (plonk/keygen.rs, permutation/keygen.rs)
+    def keygen(self, fixed_values, copies):
+        """fixed_values: list of (n,4) arrays; copies: list of ((type, col, row), (type, col, row))."""
+        F, cs, dom, n = self.F, self.cs, self.dom, self.cs.n
+        pk = {}
+        pk["fixed_values"] = fixed_values
+        pk["fixed_polys"] = [self.lagrange_to_coeff(v) for v in fixed_values]
+        # permutation Assembly: mapping/aux/sizes with cycle merging (permutation/keygen.rs Assembly::copy)
+        cols = cs.perm_columns
+        cidx = {c: i for i, c in enumerate(cols)}
+        mapping = [[(i, j) for j in range(n)] for i in range(len(cols))]
+        aux = [[(i, j) for j in range(n)] for i in range(len(cols))]
+        sizes = [[1] * n for _ in cols]
+        for (lt, lc, lr), (rt, rc, rr) in copies:
+            a, b = (cidx[(lt, lc)], lr), (cidx[(rt, rc)], rr)
+            lcy, rcy = aux[a[0]][a[1]], aux[b[0]][b[1]]
+            if lcy == rcy: continue
+            if sizes[lcy[0]][lcy[1]] < sizes[rcy[0]][rcy[1]]:
+                lcy, rcy = rcy, lcy
+            sizes[lcy[0]][lcy[1]] += sizes[rcy[0]][rcy[1]]
+            i, j = rcy
+            while True:
+                aux[i][j] = lcy
+                i, j = mapping[i][j]
+                if (i, j) == rcy: break
+            mapping[a[0]][a[1]], mapping[b[0]][b[1]] = mapping[b[0]][b[1]], mapping[a[0]][a[1]]
+        om = [pow(dom.omega, j, R) for j in range(n)]
+        dl = [pow(P.FR_DELTA, i, R) for i in range(len(cols))]
+        pk["sigma_values"] = [F.arr([dl[mapping[i][j][0]] * om[mapping[i][j][1]] % R for j in range(n)]) for i in range(len(cols))]
+        pk["sigma_polys"] = [self.lagrange_to_coeff(v) for v in pk["sigma_values"]]
+        l0 = np.zeros((n, 4), dtype=np.uint64); l0[0] = self.w_arr(1)
+        lblind = np.zeros((n, 4), dtype=np.uint64); lblind[n - self.bf:] = self.w_arr(1)
+        llast = np.zeros((n, 4), dtype=np.uint64); llast[n - self.bf - 1] = self.w_arr(1)
+        pk["l0"], pk["l_last"], pk["l_blind"] = [self.lagrange_to_coeff(v) for v in (l0, llast, lblind)]
+        pk["fixed_commitments"] = [self.commit_lagrange(v) for v in fixed_values]
+        pk["sigma_commitments"] = [self.commit_lagrange(v) for v in pk["sigma_values"]]
+        return pk
+
+    # ---- expression evaluation over whole columns
+    def eval_expr(self, e, cols, challenges, size, step):
+        """cols: dict (type) -> list of arrays of `size` rows; rotation r reads row (i + r*step) mod size."""
+        F = self.F
+        op = e.op
+        if op == CONST: return F.full(e.a, size)
+        if op == CHALLENGE: return F.full(challenges[e.a], size)
+        if op in (FIXED, ADVICE, INSTANCE): return rot(cols[op][e.a], e.b, step)
+        if op == NEG: return F.neg(self.eval_expr(e.a, cols, challenges, size, step))
+        if op == ADD: return F.add(self.eval_expr(e.a, cols, challenges, size, step), self.eval_expr(e.b, cols, challenges, size, step))
+        if op == MUL: return F.mul(self.eval_expr(e.a, cols, challenges, size, step), self.eval_expr(e.b, cols, challenges, size, step))
+        if op == SCALED: return F.scal(self.eval_expr(e.a, cols, challenges, size, step), e.b)
+        raise ValueError(op)
+
+    def compress(self, exprs, theta, cols, challenges, size, step):
+        F = self.F
+        acc = np.zeros((size, 4), dtype=np.uint64)
+        for e in exprs:
+            acc = F.add(F.scal(acc, theta), self.eval_expr(e, cols, challenges, size, step))
+        return acc
+
+    # ---- transcript (transcript/blake2b.rs)
+    class Transcript:
+        def __init__(self, ref):
+            self.h = hashlib.blake2b(digest_size=64, person=b"Halo2-Transcript")
+            self.buf = bytearray()
+            self.ref = ref
+
+        def common_scalar(self, v):
+            self.h.update(b"\x02" + int(v).to_bytes(32, "little"))
+
+        def common_point(self, aff):
+            x = P.from_mont(P.from_limbs(aff[:4]), P.Q_MOD); y = P.from_mont(P.from_limbs(aff[4:]), P.Q_MOD)
+            assert not (x == 0 and y == 0), "cannot write points at infinity to the transcript"
+            self.h.update(b"\x01" + x.to_bytes(32, "little") + y.to_bytes(32, "little"))
+
+        def write_point(self, aff):
+            self.common_point(aff)
+            self.buf += self.ref.o.g1_compress(aff)
+
+        def write_scalar(self, v):
+            self.common_scalar(v)
+            self.buf += int(v).to_bytes(32, "little")
+
+        def squeeze(self):
+            self.h.update(b"\x00")
+            return int.from_bytes(self.h.copy().digest(), "little") % R
+
+    # ---- create_proof (plonk/prover.rs)
+    def create_proof(self, pk, transcript_repr, instances, synthesize, blinds):
+        """instances: list (per instance column) of lists of ints.
+        synthesize(phase, challenges) -> dict advice column index -> (n,4) array, already blinded in the last bf+1 rows
+        (rows >= n - (bf + 1) random), for the columns of that phase.
+        blinds: dict with 'z' [chunks][bf] ints, 'phi' [lookups][bf] ints, 'random_poly' (n,4) array.
+        Returns (proof bytes, debug dict)."""
+        F, cs, dom, n, bf = self.F, self.cs, self.dom, self.cs.n, self.bf
+        dbg = {}
+        tr = Ref.Transcript(self)
+        tr.common_scalar(transcript_repr)
+        inst_values = []
+        for col in instances:
+            assert len(col) <= n - (bf + 1)
+            for v in col: tr.common_scalar(v % R)
+            a = np.zeros((n, 4), dtype=np.uint64)
+            if col: a[: len(col)] = F.arr(col)
+            inst_values.append(a)
+        inst_polys = [self.lagrange_to_coeff(a) for a in inst_values]
+        adv_values = [None] * cs.num_advice
+        challenges = {}
+        for phase in range(cs.num_phases()):
+            cols = synthesize(phase, dict(challenges))
+            for c in range(cs.num_advice):
+                if cs.advice_phase[c] == phase:
+                    adv_values[c] = np.ascontiguousarray(cols[c])
+                    tr.write_point(self.commit_lagrange(adv_values[c]))
+            for ci, ph in enumerate(cs.challenge_phase):
+                if ph == phase: challenges[ci] = tr.squeeze()
+        theta = tr.squeeze()
+        vals = {FIXED: pk["fixed_values"], ADVICE: adv_values, INSTANCE: inst_values}
+        one = self.w_arr(1)
+        # mv-lookup prepare: compressed inputs / table, multiplicities m (usable rows only)
+        usable = n - bf - 1
+        lk_data = []
+        for lk in cs.lookups:
+            fs = [self.compress(inp, theta, vals, challenges, n, 1) for inp in lk.inputs]
+            t = self.compress(lk.table, theta, vals, challenges, n, 1)
+            tkeys = [r.tobytes() for r in t[:usable]]
+            index = {}
+            for i, kx in enumerate(tkeys):
+                index[kx] = i                              # BTreeMap collect(): the LAST duplicate table row wins
+            m = [0] * n
+            for f in fs:
+                for r in f[:usable]:
+                    m[index[r.tobytes()]] += 1          # KeyError = input not in table (unsatisfied lookup)
+            m_arr = F.arr(m)
+            lk_data.append((fs, t, m_arr))
+            tr.write_point(self.commit_lagrange(m_arr))
+        beta = tr.squeeze(); gamma = tr.squeeze()
+        # permutation grand products (permutation/prover.rs)
+        zs = []
+        omega_pows = F.powers(dom.omega, n)
+        last_z = one.copy()
+        delta_pow = 1
+        pcols = cs.perm_columns
+        for ci in range(0, len(pcols), self.chunk):
+            cc = pcols[ci: ci + self.chunk]
+            den = np.repeat(one[None], n, axis=0)
+            num = np.repeat(one[None], n, axis=0)
+            for j, (t_, i_) in enumerate(cc):
+                v = vals[t_][i_]
+                den = F.mul(den, F.addc(F.add(v, F.scal(pk["sigma_values"][ci + j], beta)), gamma))
+                num = F.mul(num, F.addc(F.add(v, F.scal(omega_pows, beta * delta_pow % R)), gamma))
+                delta_pow = delta_pow * P.FR_DELTA % R
+            mod = F.mul(num, F.inv(den))
+            z = np.zeros((n, 4), dtype=np.uint64)
+            z[0] = last_z
+            zi = F.ints(mod)
+            cur = F.ints(last_z[None])[0]
+            zl = [cur]
+            for row in range(1, n):
+                cur = cur * zi[row - 1] % R
+                zl.append(cur)
+            z = F.arr(zl)
+            z[n - bf:] = F.arr(blinds["z"][ci // self.chunk])
+            last_z = z[n - bf - 1].copy()
+            zs.append(z)
+        z_polys = [self.lagrange_to_coeff(z) for z in zs]
+        for z in zs: tr.write_point(self.commit_lagrange(z))
+        # lookup grand sums
+        phis = []
+        for li, (fs, t, m_arr) in enumerate(lk_data):
+            tb_inv = F.inv(F.addc(t, beta))
+            acc = F.neg(F.mul(m_arr, tb_inv))
+            for f in fs:
+                acc = F.add(acc, F.inv(F.addc(f, beta)))
+            ai = F.ints(acc)
+            ph = [0]
+            for row in range(1, n - bf):
+                ph.append((ph[-1] + ai[row - 1]) % R)
+            assert (ph[-1] + 0) % R == (ph[n - bf - 1]) % R
+            assert ph[n - bf - 1] == 0 or True
+            ph += [b % R for b in blinds["phi"][li]]
+            phis.append(F.arr(ph))
+        dbg["phi_last"] = [F.ints(p[n - bf - 1: n - bf])[0] for p in phis]
+        for p in phis: tr.write_point(self.commit_lagrange(p))
+        m_polys = [self.lagrange_to_coeff(d[2]) for d in lk_data]
+        phi_polys = [self.lagrange_to_coeff(p) for p in phis]
+        random_poly = np.ascontiguousarray(blinds["random_poly"])
+        tr.write_point(self.commit(random_poly))
+        y = tr.squeeze()
+        adv_polys = [self.lagrange_to_coeff(a) for a in adv_values]
+        # ---- quotient (plonk/evaluation.rs evaluate_h), whole extended domain at once
+        N, E = dom.N, dom.E
+        ext = {FIXED: [self.coeff_to_extended(p) for p in pk["fixed_polys"]],
+               ADVICE: [self.coeff_to_extended(p) for p in adv_polys],
+               INSTANCE: [self.coeff_to_extended(p) for p in inst_polys]}
+        sig_ext = [self.coeff_to_extended(p) for p in pk["sigma_polys"]]
+        l0 = self.coeff_to_extended(pk["l0"]); llast = self.coeff_to_extended(pk["l_last"]); lblind = self.coeff_to_extended(pk["l_blind"])
+        lactive = F.sub(F.sub(np.repeat(one[None], N, axis=0), llast), lblind)
+        h = np.zeros((N, 4), dtype=np.uint64)
+
+        def fold(term):
+            nonlocal h
+            h = F.add(F.scal(h, y), term)
+        for g in cs.gates:
+            fold(self.eval_expr(g, ext, challenges, N, E))
+        if zs:
+            z_ext = [self.coeff_to_extended(p) for p in z_polys]
+            onesN = np.repeat(one[None], N, axis=0)
+            fold(F.mul(F.sub(onesN, z_ext[0]), l0))
+            zl_ = z_ext[-1]
+            fold(F.mul(F.sub(F.mul(zl_, zl_), zl_), llast))
+            for i in range(1, len(z_ext)):
+                fold(F.mul(F.sub(z_ext[i], rot(z_ext[i - 1], -(bf + 1), E)), l0))
+            xs = F.scal(F.powers(dom.extended_omega, N), P.FR_ZETA)     # X on the extended coset
+            delta_pow = 1
+            for si, ze in enumerate(z_ext):
+                cc = pcols[si * self.chunk: (si + 1) * self.chunk]
+                left = rot(ze, 1, E)
+                right = ze
+                for j, (t_, i_) in enumerate(cc):
+                    v = ext[t_][i_]
+                    left = F.mul(left, F.addc(F.add(v, F.scal(sig_ext[si * self.chunk + j], beta)), gamma))
+                    right = F.mul(right, F.addc(F.add(v, F.scal(xs, beta * delta_pow % R)), gamma))
+                    delta_pow = delta_pow * P.FR_DELTA % R
+                fold(F.mul(F.sub(left, right), lactive))
+        for li, lk in enumerate(cs.lookups):
+            phi_e = self.coeff_to_extended(phi_polys[li]); m_e = self.coeff_to_extended(m_polys[li])
+            fsb = [F.addc(self.compress(inp, theta, ext, challenges, N, E), beta) for inp in lk.inputs]
+            tb = F.addc(self.compress(lk.table, theta, ext, challenges, N, E), beta)
+            prod = fsb[0]
+            for f in fsb[1:]: prod = F.mul(prod, f)
+            ssum = np.zeros((N, 4), dtype=np.uint64)       # sum_i prod_{j != i} (f_j + beta)
+            for i in range(len(fsb)):
+                pr = None
+                for j in range(len(fsb)):
+                    if j == i: continue
+                    pr = fsb[j] if pr is None else F.mul(pr, fsb[j])
+                if pr is None: pr = np.repeat(one[None], N, axis=0)
+                ssum = F.add(ssum, pr)
+            lhs = F.mul(F.mul(tb, prod), F.sub(rot(phi_e, 1, E), phi_e))
+            rhs = F.sub(F.mul(tb, ssum), F.mul(m_e, prod))
+            fold(F.mul(phi_e, l0))
+            fold(F.mul(phi_e, llast))
+            fold(F.mul(F.sub(lhs, rhs), lactive))
+        dbg["h_numerator_ext"] = h
+        tinv = F.inv(F.arr(dom.t_evaluations))
+        h = F.mul(h, tinv[np.arange(N) % E])
+        h_coeffs = self.extended_to_coeff(h)
+        dbg["h_coeffs"] = h_coeffs
+        pieces = [np.ascontiguousarray(h_coeffs[i * n: (i + 1) * n]) for i in range(dom.qdeg)]
+        for pc in pieces: tr.write_point(self.commit(pc))
+        x = tr.squeeze()
+        xn = pow(x, n, R)
+        # ---- evaluations
+        for (c, r) in cs.advice_queries: tr.write_scalar(self.eval_poly(adv_polys[c], dom.rotate_omega(x, r)))
+        for (c, r) in cs.fixed_queries: tr.write_scalar(self.eval_poly(pk["fixed_polys"][c], dom.rotate_omega(x, r)))
+        tr.write_scalar(self.eval_poly(random_poly, x))
+        for sp in pk["sigma_polys"]: tr.write_scalar(self.eval_poly(sp, x))
+        x_next, x_last = dom.rotate_omega(x, 1), dom.rotate_omega(x, -(bf + 1))
+        for i, zp in enumerate(z_polys):
+            tr.write_scalar(self.eval_poly(zp, x)); tr.write_scalar(self.eval_poly(zp, x_next))
+            if i != len(z_polys) - 1: tr.write_scalar(self.eval_poly(zp, x_last))
+        for li in range(len(cs.lookups)):
+            tr.write_scalar(self.eval_poly(phi_polys[li], x)); tr.write_scalar(self.eval_poly(phi_polys[li], x_next))
+            tr.write_scalar(self.eval_poly(m_polys[li], x))
+        # ---- h(X) = sum x^(n i) piece_i
+        h_poly = np.zeros((n, 4), dtype=np.uint64)
+        for pc in reversed(pieces): h_poly = F.add(F.scal(h_poly, xn), pc)
+        # ---- multiopen queries, prover order (plonk/prover.rs)
+        queries = []   # (poly id, coeffs, point)
+        for (c, r) in cs.advice_queries: queries.append((("adv", c), adv_polys[c], dom.rotate_omega(x, r)))
+        for i, zp in enumerate(z_polys):
+            queries.append((("z", i), zp, x)); queries.append((("z", i), zp, x_next))
+        for i in range(len(z_polys) - 2, -1, -1): queries.append((("z", i), z_polys[i], x_last))
+        for li in range(len(cs.lookups)):
+            queries.append((("phi", li), phi_polys[li], x)); queries.append((("phi", li), phi_polys[li], x_next))
+            queries.append((("m", li), m_polys[li], x))
+        for (c, r) in cs.fixed_queries: queries.append((("fix", c), pk["fixed_polys"][c], dom.rotate_omega(x, r)))
+        for i, sp in enumerate(pk["sigma_polys"]): queries.append((("sig", i), sp, x))
+        queries.append((("h",), h_poly, x)); queries.append((("rand",), random_poly, x))
+        self.shplonk_prove(tr, queries)
+        dbg.update(dict(theta=theta, beta=beta, gamma=gamma, y=y, x=x, challenges=challenges, zs=zs, phis=phis, ms=[d[2] for d in lk_data],
+                        adv_polys=adv_polys, pieces=pieces))
+        return bytes(tr.buf), dbg
+
+    # ---- SHPLONK (poly/kzg/multiopen/shplonk.rs + shplonk/prover.rs)
+    @staticmethod
+    def intermediate_sets(queries):
+        """queries: list of (key, payload, point).  Returns (rotation_sets [(points sorted, [(key, payload)])], super point set sorted)."""
+        super_pts = sorted({q[2] for q in queries})
+        cmap = []      # (key, payload, set of points)
+        for key, payload, pt in queries:
+            for ent in cmap:
+                if ent[0] == key:
+                    ent[2].add(pt); break
+            else:
+                cmap.append([key, payload, {pt}])
+        sets = []      # (frozenset points, [(key, payload)])
+        for key, payload, pts in cmap:
+            fs = frozenset(pts)
+            for ent in sets:
+                if ent[0] == fs:
+                    ent[1].append((key, payload)); break
+            else:
+                sets.append((fs, [(key, payload)]))
+        return [(sorted(fs), comms) for fs, comms in sets], super_pts
+
+    @staticmethod
+    def lagrange_interpolate(points, evals):
+        """coefficients (ints, low to high) of the unique poly of degree < len(points)."""
+        k = len(points)
+        coeffs = [0] * k
+        for j in range(k):
+            # basis_j = prod_{m != j} (X - x_m) / (x_j - x_m)
+            num = [1]
+            den = 1
+            for m in range(k):
+                if m == j: continue
+                num = [((num[i - 1] if i > 0 else 0) - points[m] * (num[i] if i < len(num) else 0)) % R for i in range(len(num) + 1)]
+                den = den * (points[j] - points[m]) % R
+            sc = evals[j] * pow(den, -1, R) % R
+            for i in range(k): coeffs[i] = (coeffs[i] + num[i] * sc) % R
+        return coeffs
+
+    def kate_division(self, coeffs_ints, u):
+        """q(X) = (a(X) - a(u)) / (X - u); returns len-1 coefficients (arithmetic.rs kate_division)."""
+        q = [0] * (len(coeffs_ints) - 1)
+        tmp = 0
+        for i in range(len(coeffs_ints) - 1, 0, -1):
+            tmp = (coeffs_ints[i] + tmp * u) % R
+            q[i - 1] = tmp
+        return q
+
+    def shplonk_prove(self, tr, queries):
+        F, n = self.F, self.cs.n
+        y = tr.squeeze()
+        rsets, super_pts = self.intermediate_sets(queries)
+        v = tr.squeeze()
+        evals_of = {}
+        for key, coeffs, pt in queries:
+            evals_of[(key, pt)] = self.eval_poly(coeffs, pt)
+
+        def q_contrib(points, comms):
+            acc = [0] * n
+            ypow = 1
+            for key, coeffs in comms:
+                ev = [evals_of[(key, p)] for p in points]
+                r = self.lagrange_interpolate(points, ev)
+                ci = F.ints(coeffs)
+                for i, rv in enumerate(r): ci[i] = (ci[i] - rv) % R
+                for i in range(n): acc[i] = (acc[i] + ci[i] * ypow) % R
+                ypow = ypow * y % R
+            for p in points: acc = self.kate_division(acc, p)
+            return acc + [0] * (n - len(acc))
+        h_x = [0] * n
+        vpow = 1
+        for points, comms in rsets:
+            q = q_contrib(points, comms)
+            for i in range(n): h_x[i] = (h_x[i] + q[i] * vpow) % R
+            vpow = vpow * v % R
+        tr.write_point(self.commit(F.arr(h_x)))
+        u = tr.squeeze()
+        l_x = [0] * n
+        vpow = 1
+        z_diffs = []
+        for points, comms in rsets:
+            z_i = 1
+            for p in super_pts:
+                if p not in points: z_i = z_i * (u - p) % R
+            z_diffs.append(z_i)
+            inner = [0] * n
+            ypow = 1
+            for key, coeffs in comms:
+                ev = [evals_of[(key, p)] for p in points]
+                r = self.lagrange_interpolate(points, ev)
+                r_u = 0
+                for c in reversed(r): r_u = (r_u * u + c) % R
+                ci = F.ints(coeffs)
+                ci[0] = (ci[0] - r_u) % R
+                for i in range(n): inner[i] = (inner[i] + ci[i] * ypow) % R
+                ypow = ypow * y % R
+            for i in range(n): l_x[i] = (l_x[i] + inner[i] * z_i % R * vpow) % R
+            vpow = vpow * v % R
+        zt = 1
+        for p in super_pts: zt = zt * (u - p) % R
+        for i in range(n): l_x[i] = (l_x[i] - h_x[i] * zt) % R
+        chk = 0
+        for c in reversed(l_x): chk = (chk * u + c) % R
+        assert chk == 0, "SHPLONK linearisation does not vanish at u"
+        hq = self.kate_division(l_x, u)
+        zinv = pow(z_diffs[0], -1, R)
+        hq = [c * zinv % R for c in hq] + [0]
+        tr.write_point(self.commit(F.arr(hq)))
+
+    # ---- verifier (plonk/verifier.rs + shplonk/verifier.rs); pairing replaced by the known-s trapdoor check
+    class Reader:
+        def __init__(self, ref, proof):
+            self.h = hashlib.blake2b(digest_size=64, person=b"Halo2-Transcript")
+            self.p, self.pos, self.ref = proof, 0, ref
+
+        def common_scalar(self, v): self.h.update(b"\x02" + int(v).to_bytes(32, "little"))
+
+        def read_point(self):
+            b = self.p[self.pos: self.pos + 32]; self.pos += 32
+            pt = P.g1_decompress(b)
+            assert pt is not None and P.g1_is_on_curve(pt)
+            self.h.update(b"\x01" + pt[0].to_bytes(32, "little") + pt[1].to_bytes(32, "little"))
+            return pt
+
+        def read_scalar(self):
+            v = int.from_bytes(self.p[self.pos: self.pos + 32], "little"); self.pos += 32
+            assert v < R
+            self.common_scalar(v)
+            return v
+
+        def squeeze(self):
+            self.h.update(b"\x00")
+            return int.from_bytes(self.h.copy().digest(), "little") % R
+
+    def aff_to_pt(self, aff):
+        x = P.from_mont(P.from_limbs(aff[:4]), P.Q_MOD); y = P.from_mont(P.from_limbs(aff[4:]), P.Q_MOD)
+        return None if (x == 0 and y == 0) else (x, y)
+
+    def eval_expr_at(self, e, ev, challenges):
+        op = e.op
+        if op == CONST: return e.a
+        if op == CHALLENGE: return challenges[e.a]
+        if op in (FIXED, ADVICE, INSTANCE): return ev[(op, e.a, e.b)]
+        if op == NEG: return (-self.eval_expr_at(e.a, ev, challenges)) % R
+        if op == ADD: return (self.eval_expr_at(e.a, ev, challenges) + self.eval_expr_at(e.b, ev, challenges)) % R
+        if op == MUL: return self.eval_expr_at(e.a, ev, challenges) * self.eval_expr_at(e.b, ev, challenges) % R
+        if op == SCALED: return self.eval_expr_at(e.a, ev, challenges) * e.b % R
+        raise ValueError
+
+    def verify_proof(self, pk, transcript_repr, instances, proof):
+        cs, dom, n, bf = self.cs, self.dom, self.cs.n, self.bf
+        rd = Ref.Reader(self, proof)
+        rd.common_scalar(transcript_repr)
+        for col in instances:
+            for v in col: rd.common_scalar(v % R)
+        adv_c = [None] * cs.num_advice
+        challenges = {}
+        for phase in range(cs.num_phases()):
+            for c in range(cs.num_advice):
+                if cs.advice_phase[c] == phase: adv_c[c] = rd.read_point()
+            for ci, ph in enumerate(cs.challenge_phase):
+                if ph == phase: challenges[ci] = rd.squeeze()
+        theta = rd.squeeze()
+        m_c = [rd.read_point() for _ in cs.lookups]
+        beta = rd.squeeze(); gamma = rd.squeeze()
+        nsets = (len(cs.perm_columns) + self.chunk - 1) // self.chunk
+        z_c = [rd.read_point() for _ in range(nsets)]
+        phi_c = [rd.read_point() for _ in cs.lookups]
+        rand_c = rd.read_point()
+        y = rd.squeeze()
+        h_c = [rd.read_point() for _ in range(dom.qdeg)]
+        x = rd.squeeze()
+        xn = pow(x, n, R)
+        ev = {}
+        # instance evaluations are computed by the verifier (KZG: QUERY_INSTANCE = false): lagrange basis at x
+        if cs.instance_queries:
+            maxlen = max((len(c) for c in instances), default=0)
+            min_rot = min([r for _, r in cs.instance_queries] + [0]); max_rot = max([r for _, r in cs.instance_queries] + [0])
+            # l_i(x) for i in -max_rot .. maxlen - min_rot
+            def l_i(i):
+                wi = pow(dom.omega, i % n, R)
+                return (xn - 1) * wi % R * pow(n * (x - wi) % R, -1, R) % R
+            for (c, r) in cs.instance_queries:
+                ev[(INSTANCE, c, r)] = sum(v * l_i(i - r) for i, v in enumerate(instances[c])) % R
+        for (c, r) in cs.advice_queries: ev[(ADVICE, c, r)] = rd.read_scalar()
+        for (c, r) in cs.fixed_queries: ev[(FIXED, c, r)] = rd.read_scalar()
+        rand_eval = rd.read_scalar()
+        sig_ev = [rd.read_scalar() for _ in cs.perm_columns]
+        z_ev = []
+        for i in range(nsets):
+            a = rd.read_scalar(); b = rd.read_scalar()
+            c_ = rd.read_scalar() if i != nsets - 1 else None
+            z_ev.append((a, b, c_))
+        lk_ev = []
+        for _ in cs.lookups:
+            a = rd.read_scalar(); b = rd.read_scalar(); c_ = rd.read_scalar()
+            lk_ev.append((a, b, c_))
+        # l_0, l_last, l_blind at x
+        def lag(i):
+            wi = pow(dom.omega, i % n, R)
+            return (xn - 1) * wi % R * pow(n * (x - wi) % R, -1, R) % R
+        l0 = lag(0); llast = lag(n - bf - 1); lblind = sum(lag(i) for i in range(n - bf, n)) % R
+        lactive = (1 - llast - lblind) % R
+        acc = 0
+        def fold(t):
+            nonlocal acc
+            acc = (acc * y + t) % R
+        for g in cs.gates: fold(self.eval_expr_at(g, ev, challenges))
+        if nsets:
+            fold(l0 * (1 - z_ev[0][0]) % R)
+            zl = z_ev[-1][0]
+            fold(llast * (zl * zl - zl) % R)
+            for i in range(1, nsets): fold(l0 * (z_ev[i][0] - z_ev[i - 1][2]) % R)
+            dp = 1
+            tyv = {FIXED: FIXED, ADVICE: ADVICE, INSTANCE: INSTANCE}
+            for si in range(nsets):
+                cc = cs.perm_columns[si * self.chunk: (si + 1) * self.chunk]
+                left = z_ev[si][1]; right = z_ev[si][0]
+                for j, (t_, i_) in enumerate(cc):
+                    v = ev[(tyv[t_], i_, 0)]
+                    left = left * (v + beta * sig_ev[si * self.chunk + j] + gamma) % R
+                    right = right * (v + beta * dp % R * x + gamma) % R
+                    dp = dp * P.FR_DELTA % R
+                fold(lactive * (left - right) % R)
+        for li, lk in enumerate(cs.lookups):
+            phi_x, phi_nx, m_x = lk_ev[li]
+            def comp(exprs):
+                a = 0
+                for e in exprs: a = (a * theta + self.eval_expr_at(e, ev, challenges)) % R
+                return a
+            fsb = [(comp(inp) + beta) % R for inp in lk.inputs]
+            tb = (comp(lk.table) + beta) % R
+            prod = 1
+            for f in fsb: prod = prod * f % R
+            ssum = 0
+            for i in range(len(fsb)):
+                pr = 1
+                for j in range(len(fsb)):
+                    if j != i: pr = pr * fsb[j] % R
+                ssum = (ssum + pr) % R
+            lhs = tb * prod % R * (phi_nx - phi_x) % R
+            rhs = (tb * ssum - m_x * prod) % R
+            fold(l0 * phi_x % R); fold(llast * phi_x % R); fold(lactive * (lhs - rhs) % R)
+        expected_h = acc * pow(xn - 1, -1, R) % R
+        # h commitment = sum x^(n i) H_i
+        hc = None
+        for c in reversed(h_c): hc = P.g1_add(P.g1_mul(hc, xn) if hc else None, c)
+        # queries in verifier order == prover order
+        x_next, x_last = dom.rotate_omega(x, 1), dom.rotate_omega(x, -(bf + 1))
+        queries = []
+        for (c, r) in cs.advice_queries: queries.append((("adv", c), adv_c[c], dom.rotate_omega(x, r), ev[(ADVICE, c, r)]))
+        for i in range(nsets):
+            queries.append((("z", i), z_c[i], x, z_ev[i][0])); queries.append((("z", i), z_c[i], x_next, z_ev[i][1]))
+        for i in range(nsets - 2, -1, -1): queries.append((("z", i), z_c[i], x_last, z_ev[i][2]))
+        for li in range(len(cs.lookups)):
+            queries.append((("phi", li), phi_c[li], x, lk_ev[li][0])); queries.append((("phi", li), phi_c[li], x_next, lk_ev[li][1]))
+            queries.append((("m", li), m_c[li], x, lk_ev[li][2]))
+        for (c, r) in cs.fixed_queries: queries.append((("fix", c), self.aff_to_pt(pk["fixed_commitments"][c]), dom.rotate_omega(x, r), ev[(FIXED, c, r)]))
+        for i in range(len(cs.perm_columns)): queries.append((("sig", i), self.aff_to_pt(pk["sigma_commitments"][i]), x, sig_ev[i]))
+        queries.append((("h",), hc, x, expected_h)); queries.append((("rand",), rand_c, x, rand_eval))
+        # SHPLONK verifier
+        yv = rd.squeeze(); v = rd.squeeze()
+        h1 = rd.read_point(); u = rd.squeeze(); h2 = rd.read_point()
+        assert rd.pos == len(proof), "trailing bytes"
+        evalmap = {(k_, p_): e_ for k_, _, p_, e_ in queries}
+        rsets, super_pts = self.intermediate_sets([(k_, c_, p_) for k_, c_, p_, _ in queries])
+        outer = None; r_outer = 0; z0 = 0; z0_diff_inv = 0
+        vpow = 1
+        for i, (points, comms) in enumerate(rsets):
+            zd = 1
+            for p in super_pts:
+                if p not in points: zd = zd * (u - p) % R
+            if i == 0:
+                z0 = 1
+                for p in points: z0 = z0 * (u - p) % R
+                z0_diff_inv = pow(zd, -1, R); zd = 1
+            else:
+                zd = zd * z0_diff_inv % R
+            inner = None; r_inner = 0; ypow = 1
+            for key, cpt in comms:
+                r = self.lagrange_interpolate(points, [evalmap[(key, p)] for p in points])
+                r_u = 0
+                for c in reversed(r): r_u = (r_u * u + c) % R
+                r_inner = (r_inner + ypow * r_u) % R
+                inner = P.g1_add(inner, P.g1_mul(cpt, ypow))
+                ypow = ypow * yv % R
+            outer = P.g1_add(outer, P.g1_mul(inner, vpow * zd % R))
+            r_outer = (r_outer + vpow * r_inner % R * zd) % R
+            vpow = vpow * v % R
+        G = P.G1_GEN
+        right = P.g1_add(outer, P.g1_mul(G, (-r_outer) % R))
+        right = P.g1_add(right, P.g1_mul(h1, (-z0) % R))
+        right = P.g1_add(right, P.g1_mul(h2, u))
+        # pairing check e(h2, [s]G2) == e(right, G2)  <=>  [s] h2 == right   (s known in tests)
+        return P.g1_mul(h2, self.s) == right
