@@ -101,6 +101,23 @@ ZKB_API int32_t zkb_field_unop_dev(zkb_ctx *ctx, int32_t field, int32_t op, cons
 /* Montgomery batch inversion (halo2 `BatchInvert` / batch_invert_assigned): out[i] = a[i]^-1, zeros stay zero. */
 ZKB_API int32_t zkb_fr_batch_invert_dev(zkb_ctx *ctx, const uint64_t *a, uint64_t *out, uint64_t n, void *stream);
 
+/* ---- polynomial utilities around MSM/NTT (device buffers) ----------------------------------------------------
+ * zkb_fr_powers_dev        out[i] = base^i
+ * zkb_poly_eval_dev        halo2_proofs::arithmetic::eval_polynomial for `num_polys` polynomials (host array of device
+ *                          pointers, n coefficients each) at one point x; results (Montgomery) to out_host; synchronises.
+ * zkb_fr_prefix_product_dev / _sum_dev   out[0] = init, out[i+1] = out[i] (*|+) in[i]  (n outputs; the running product z of
+ *                          permutation/prover.rs and the running sum phi of mv_lookup/prover.rs)
+ * zkb_kate_division_dev    halo2_proofs::arithmetic::kate_division: q = (a(X) - a(u)) / (X - u); q has n entries, q[n-1] = 0 */
+ZKB_API int32_t zkb_fr_powers_dev(zkb_ctx *ctx, const uint64_t base[4], uint64_t n, uint64_t *out_dev, void *stream);
+ZKB_API int32_t zkb_poly_eval_dev(zkb_ctx *ctx, const uint64_t *const *polys_dev, uint32_t num_polys, uint64_t n,
+                                  const uint64_t x[4], uint64_t *out_host, void *stream);
+ZKB_API int32_t zkb_fr_prefix_product_dev(zkb_ctx *ctx, const uint64_t *in_dev, uint64_t n, const uint64_t init[4],
+                                          uint64_t *out_dev, void *stream);
+ZKB_API int32_t zkb_fr_prefix_sum_dev(zkb_ctx *ctx, const uint64_t *in_dev, uint64_t n, const uint64_t init[4],
+                                      uint64_t *out_dev, void *stream);
+ZKB_API int32_t zkb_kate_division_dev(zkb_ctx *ctx, const uint64_t *a_dev, uint64_t n, const uint64_t u[4],
+                                      uint64_t *q_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

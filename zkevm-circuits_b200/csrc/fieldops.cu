@@ -56,6 +56,15 @@ __global__ void batch_invert_kernel(const Fr *__restrict__ a, Fr *__restrict__ o
     }
 }
 
+int32_t batch_invert_device(zkb_ctx *ctx, const Fr *a, Fr *out, uint64_t n, cudaStream_t st) {
+    if (n == 0) return ZKB_OK;
+    const uint64_t threads_total = (n + BI_CHUNK - 1) / BI_CHUNK;
+    batch_invert_kernel<<<(unsigned)((threads_total + 127) / 128), 128, 0, st>>>(a, out, n);
+    ctx->launches++;
+    ZKB_CUDA(cudaGetLastError());
+    return ZKB_OK;
+}
+
 }  // namespace zkb
 using namespace zkb;
 
@@ -91,10 +100,5 @@ extern "C" int32_t zkb_field_unop_dev(zkb_ctx *ctx, int32_t field, int32_t op, c
 extern "C" int32_t zkb_fr_batch_invert_dev(zkb_ctx *ctx, const uint64_t *a, uint64_t *out, uint64_t n, void *stream) {
     ZKB_ARG(ctx && a && out && a != out);
     if (n == 0) return ZKB_OK;
-    cudaStream_t st = pick_stream(ctx, stream);
-    const uint64_t threads_total = (n + BI_CHUNK - 1) / BI_CHUNK;
-    batch_invert_kernel<<<(unsigned)((threads_total + 127) / 128), 128, 0, st>>>((const Fr *)a, (Fr *)out, n);
-    ctx->launches++;
-    ZKB_CUDA(cudaGetLastError());
-    return ZKB_OK;
+    return batch_invert_device(ctx, (const Fr *)a, (Fr *)out, n, pick_stream(ctx, stream));
 }

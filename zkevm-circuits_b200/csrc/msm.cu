@@ -16,7 +16,6 @@
 //      segment partials are tree-reduced per window, and the W window sums are combined by Horner doubling.
 //   Work is dominated by n*W mixed additions = n*W*10 Fq multiplies: bound by the integer-multiply pipe.
 #include "common.cuh"
-#include "g1.cuh"
 #include <string.h>
 
 namespace zkb {

@@ -38,6 +38,7 @@ struct PassArgs {
     const Fr *tw_lo;
     const Fr *tw_hi;
     const Fr *scale;
+    const Fr *in_scale;  // optional per-element input multiplier (first pass only): coset scaling tables
 };
 
 __device__ __forceinline__ Fr smem_ld(const uint4 *lo, const uint4 *hi, uint32_t i) {
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const Fr *__restrict__ in
             const uint32_t m = (uint32_t)(idx % 3);
             if (m) v = fp_mul(v, zeta_pow(m));
         }
+        if (p.in_scale) v = fp_mul(v, fp_load(p.in_scale + idx));
         smem_st(lo, hi, j, v);
     }
     __syncthreads();
@@ -206,7 +208,8 @@ static int32_t get_plan(zkb_ctx *ctx, uint32_t log_n, const Fr &omega, NttPlan *
 
 static bool g_attr_set = false;
 
-int32_t ntt_fr_device(zkb_ctx *ctx, Fr *data, uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta, cudaStream_t st) {
+int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta,
+                      const Fr *d_in_scale, cudaStream_t st) {
     ZKB_ARG(log_n <= 3 * NTT_MAX_BITS && log_n <= 28);
     ZKB_ARG(coset_zeta >= 0 && coset_zeta <= 2);
     NttPlan *plan = nullptr;
@@ -261,10 +264,11 @@ int32_t ntt_fr_device(zkb_ctx *ctx, Fr *data, uint32_t log_n, const Fr &omega, c
         p.tw_lo = (ps == 0) ? tw_lo : plan->tw_lo;
         p.tw_hi = plan->tw_hi;
         p.scale = d_scale;
+        p.in_scale = (ps == 0) ? d_in_scale : nullptr;
         const Fr *src;
         Fr *dst;
-        if (plan->npass == 1) { src = data; dst = data; }
-        else if (ps == 0) { src = data; dst = scratch; }
+        if (plan->npass == 1) { src = src_data; dst = data; }
+        else if (ps == 0) { src = src_data; dst = scratch; }
         else if (p.is_final) { src = scratch; dst = data; }
         else { src = scratch; dst = scratch; }
         const uint32_t A = 1u << a;
@@ -301,7 +305,7 @@ extern "C" int32_t zkb_ntt_fr_dev(zkb_ctx *ctx, uint64_t *data_dev, uint32_t log
     Fr w, sc;
     memcpy(w.l, omega, 32);
     if (scale) memcpy(sc.l, scale, 32);
-    return ntt_fr_device(ctx, (Fr *)data_dev, log_n, w, scale ? &sc : nullptr, coset_zeta, pick_stream(ctx, stream));
+    return ntt_fr_device(ctx, (const Fr *)data_dev, (Fr *)data_dev, log_n, w, scale ? &sc : nullptr, coset_zeta, nullptr, pick_stream(ctx, stream));
 }
 
 extern "C" int32_t zkb_ntt_fr_host(zkb_ctx *ctx, uint64_t *data_host, uint32_t log_n, const uint64_t omega[4], const uint64_t *scale,
