@@ -118,6 +118,43 @@ ZKB_API int32_t zkb_fr_prefix_sum_dev(zkb_ctx *ctx, const uint64_t *in_dev, uint
 ZKB_API int32_t zkb_kate_division_dev(zkb_ctx *ctx, const uint64_t *a_dev, uint64_t n, const uint64_t u[4],
                                       uint64_t *q_dev, void *stream);
 
+/* ---- create_proof: device-resident proving session --------------------------------------------------------------
+ * Replaces the body of halo2_proofs::plonk::create_proof::<KZGCommitmentScheme<Bn256>, ProverSHPLONK, Challenge255, R,
+ * Blake2bWrite, C> (plonk/prover.rs; called at circuit-benchmarks/src/super_circuit.rs:117-132 and, through
+ * snark_verifier_sdk::gen_snark_shplonk, at prover/src/common/prover/utils.rs:31).  `Circuit::synthesize`, the RNG and
+ * vk.transcript_repr stay on the caller's side: advice columns arrive phase by phase already blinded (rows >= n - (bf+1)
+ * random), blinding scalars for z / phi and the vanishing argument's random polynomial are passed in.
+ *
+ * CSF blob (little-endian u32 words) -- the flattened plonk::ConstraintSystem after selector compression and
+ * chunk_lookups():  [0] magic 'ZSF1' 0x3146535a [1] k [2] num_fixed [3] num_advice [4] num_instance [5] num_challenges
+ *   [6] blinding_factors [7] cs.degree() [8] num_phases [9] n_nodes [10] n_consts [11] n_gates [12] n_lookups
+ *   [13] n_permutation_columns [14] n_advice_queries [15] n_fixed_queries [16] n_instance_queries [17] reserved, then
+ *   advice_phase[num_advice], challenge_phase[num_challenges], nodes[n_nodes] x (op, a, b), consts[n_consts] x 8 (Fr,
+ *   Montgomery), gates[n_gates] (node ids), per lookup: (n_input_sets, width, input node ids..., table node ids),
+ *   permutation columns x (type, index), advice / fixed / instance queries x (column, rotation as i32).
+ *   node ops: 0 CONST(a = const idx) 1 FIXED(a = col, b = rot) 2 ADVICE 3 INSTANCE 4 CHALLENGE(a = idx) 5 NEG(a)
+ *   6 ADD(a, b) 7 MUL(a, b) 8 SCALED(a = node, b = const idx); children precede parents; column type codes 1/2/3.
+ * zkb_pk_create      ProvingKey material: fixed and permutation-sigma column VALUES (host pointers, n x Fr each), SRS
+ *                    g / g_lagrange (n x G1Affine); polynomial forms, l_0 / l_last / l_blind are derived on the device.
+ * zkb_prove_begin    absorbs vk.transcript_repr and the instance values (KZG: QUERY_INSTANCE = false)
+ * zkb_prove_advice_phase   commits the advice columns of `phase` (pointers of other phases are ignored), returns the
+ *                    challenges squeezed after that phase in challenges_out[num_challenges][4] (Montgomery Fr)
+ * zkb_prove_finish   lookups -> permutation -> vanishing -> quotient -> evaluations -> SHPLONK; z_blinds
+ *                    [n_sets][bf], phi_blinds [n_lookups][bf], random_poly [n] are Montgomery Fr arrays on the host.
+ *                    proof_out may be NULL to query the length.                                                       */
+typedef struct zkb_pk zkb_pk;
+typedef struct zkb_session zkb_session;
+ZKB_API int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
+                              const uint64_t *const *sigma_values, const uint64_t *g, const uint64_t *g_lagrange, zkb_pk **out);
+ZKB_API int32_t zkb_pk_destroy(zkb_pk *pk);
+ZKB_API int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4], const uint64_t *const *instance_values,
+                                const uint32_t *instance_lens, zkb_session **out);
+ZKB_API int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const uint64_t *const *advice_columns,
+                                       uint64_t *challenges_out);
+ZKB_API int32_t zkb_prove_finish(zkb_session *s, const uint64_t *z_blinds, const uint64_t *phi_blinds,
+                                 const uint64_t *random_poly, uint8_t *proof_out, uint64_t proof_cap, uint64_t *proof_len);
+ZKB_API int32_t zkb_session_destroy(zkb_session *s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,1070 @@
+// prover.cu -- device-resident create_proof: host orchestration (C++) over the CUDA kernels.
+//
+// Mirrors halo2_proofs 1.1.0 (scroll-tech/halo2 v1.1 @ e5ddf67) plonk/prover.rs `create_proof` for
+// KZGCommitmentScheme<Bn256> + ProverSHPLONK + Blake2bWrite/Challenge255, the instantiation the reference uses at
+// circuit-benchmarks/src/super_circuit.rs:117-132 and circuit-benchmarks/src/packed_multi_keccak.rs:72-87:
+//   transcript order, mv-lookup (logUp) argument (plonk/mv_lookup/prover.rs), permutation argument
+//   (plonk/permutation/prover.rs), vanishing argument (plonk/vanishing/prover.rs), quotient numerator term order
+//   (plonk/evaluation.rs evaluate_h), evaluation order and SHPLONK multi-open (poly/kzg/multiopen/shplonk/prover.rs).
+// The proof layout / evaluation order / constraint formulas are the ones visible in the reference fixture
+// aggregator/data/batch-task.json (see tests/golden and SURVEY.md appendix B).
+//
+// What crosses the boundary (include/zkb200.h, `zkb_pk_*`, `zkb_prove_*`): the constraint system as a flat "CSF" blob,
+// fixed / sigma column values, the SRS, per-phase advice columns (already blinded by the caller), blinding scalars and
+// vk.transcript_repr (Rust-specific derivations, SURVEY.md hard part 1).  Everything else stays in HBM: columns,
+// polynomials, coset evaluations, the quotient; only 64-byte commitments and 32-byte evaluations return to the host.
+//
+// B200 design points (not upstream's): the quotient is evaluated coset-part by coset-part (extended domain = E cosets of
+// size n) by ONE fused interpreter kernel per part; all scans / inversions / evaluations are parallel kernels.
+#include "common.cuh"
+#include "expr.cuh"
+#include "blake2b.h"
+#include <algorithm>
+#include <memory>
+#include <string.h>
+
+namespace zkb {
+
+int32_t expr_run_device(zkb_ctx *ctx, const Instr *d_code, uint32_t ncode, int nregs, const Fr *const *d_cols, const Fr *d_consts,
+                        Fr *const *d_outs, uint32_t log_n, uint32_t out_stride, uint32_t out_offset, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------- CSF
+enum { N_CONST = 0, N_FIXED = 1, N_ADVICE = 2, N_INSTANCE = 3, N_CHALLENGE = 4, N_NEG = 5, N_ADD = 6, N_MUL = 7, N_SCALED = 8 };
+constexpr uint32_t CSF_MAGIC = 0x3146535au;
+
+struct CsfLookup {
+    std::vector<std::vector<uint32_t>> inputs;
+    std::vector<uint32_t> table;
+};
+struct Csf {
+    uint32_t k = 0, nf = 0, na = 0, ni = 0, nch = 0, bf = 0, d = 0, nphases = 0;
+    std::vector<uint32_t> adv_phase, ch_phase;
+    std::vector<std::array<uint32_t, 3>> nodes;
+    std::vector<Fr> consts;
+    std::vector<uint32_t> gates;
+    std::vector<CsfLookup> lookups;
+    std::vector<std::array<uint32_t, 2>> perm;
+    std::vector<std::array<int32_t, 2>> advq, fixq, instq;
+};
+
+static bool parse_csf(const uint32_t *w, uint64_t nw, Csf &c) {
+    if (nw < 18 || w[0] != CSF_MAGIC) { set_error("CSF: bad magic / too short"); return false; }
+    c.k = w[1]; c.nf = w[2]; c.na = w[3]; c.ni = w[4]; c.nch = w[5]; c.bf = w[6]; c.d = w[7]; c.nphases = w[8];
+    const uint32_t n_nodes = w[9], n_consts = w[10], n_gates = w[11], n_lookups = w[12], n_perm = w[13], n_aq = w[14], n_fq = w[15], n_iq = w[16];
+    uint64_t p = 18;
+    auto need = [&](uint64_t cnt) { return p + cnt <= nw; };
+    if (!need(c.na + c.nch)) { set_error("CSF: truncated"); return false; }
+    c.adv_phase.assign(w + p, w + p + c.na); p += c.na;
+    c.ch_phase.assign(w + p, w + p + c.nch); p += c.nch;
+    if (!need(3ull * n_nodes)) { set_error("CSF: truncated nodes"); return false; }
+    c.nodes.resize(n_nodes);
+    for (uint32_t i = 0; i < n_nodes; ++i) { c.nodes[i] = {w[p], w[p + 1], w[p + 2]}; p += 3; }
+    if (!need(8ull * n_consts)) { set_error("CSF: truncated consts"); return false; }
+    c.consts.resize(n_consts);
+    for (uint32_t i = 0; i < n_consts; ++i) { memcpy(c.consts[i].l, w + p, 32); p += 8; }
+    if (!need(n_gates)) { set_error("CSF: truncated gates"); return false; }
+    c.gates.assign(w + p, w + p + n_gates); p += n_gates;
+    c.lookups.resize(n_lookups);
+    for (uint32_t l = 0; l < n_lookups; ++l) {
+        if (!need(2)) { set_error("CSF: truncated lookups"); return false; }
+        const uint32_t nsets = w[p], width = w[p + 1];
+        p += 2;
+        if (!need((uint64_t)(nsets + 1) * width)) { set_error("CSF: truncated lookup body"); return false; }
+        c.lookups[l].inputs.resize(nsets);
+        for (uint32_t s = 0; s < nsets; ++s) { c.lookups[l].inputs[s].assign(w + p, w + p + width); p += width; }
+        c.lookups[l].table.assign(w + p, w + p + width); p += width;
+    }
+    if (!need(2ull * (n_perm + n_aq + n_fq + n_iq))) { set_error("CSF: truncated tail"); return false; }
+    c.perm.resize(n_perm);
+    for (uint32_t i = 0; i < n_perm; ++i) { c.perm[i] = {w[p], w[p + 1]}; p += 2; }
+    auto rdq = [&](std::vector<std::array<int32_t, 2>> &q, uint32_t cnt) {
+        q.resize(cnt);
+        for (uint32_t i = 0; i < cnt; ++i) { q[i] = {(int32_t)w[p], (int32_t)w[p + 1]}; p += 2; }
+    };
+    rdq(c.advq, n_aq); rdq(c.fixq, n_fq); rdq(c.instq, n_iq);
+    for (auto &nd : c.nodes) {
+        if (nd[0] > N_SCALED) { set_error("CSF: bad node op"); return false; }
+    }
+    if (c.k < 1 || c.k > 26 || c.d < 3 || c.bf < 5) { set_error("CSF: bad k / degree / blinding factors"); return false; }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------- small kernels
+__global__ void set_one_kernel(Fr *a, uint64_t idx) { fp_store(a + idx, Fr::one()); }
+__global__ void fill_range_one_kernel(Fr *a, uint64_t from, uint64_t to) {
+    uint64_t i = from + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < to) fp_store(a + i, Fr::one());
+}
+__global__ void mul_arrays_kernel(const Fr *__restrict__ a, const Fr *__restrict__ b, Fr *__restrict__ out, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) fp_store(out + i, fp_mul(fp_load(a + i), fp_load(b + i)));
+}
+// out[i] -= low[i] for i < k (subtract a low-degree polynomial given on the device)
+__global__ void sub_low_kernel(Fr *__restrict__ out, const Fr *__restrict__ low, uint32_t k) {
+    uint32_t i = threadIdx.x;
+    if (i < k) fp_store(out + i, fp_sub(fp_load(out + i), fp_load(low + i)));
+}
+
+// ---- multiplicities of the mv-lookup: open-addressing hash table keyed by the 32-byte compressed table value --------
+__device__ __forceinline__ uint32_t key_hash(const Fr &k) {
+    uint32_t h = 0x9e3779b9u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h ^= k.l[i]; h *= 0x85ebca6bu; h ^= h >> 13; }
+    return h;
+}
+__global__ void m_insert_kernel(const Fr *__restrict__ t, uint32_t usable, uint32_t *slots, uint32_t mask) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= usable) return;
+    const Fr key = fp_load(t + i);
+    uint32_t h = key_hash(key) & mask;
+    while (true) {
+        const uint32_t s = atomicCAS(&slots[h], 0u, i + 1);
+        if (s == 0) return;
+        if (fp_load(t + (s - 1)) == key) { atomicMax(&slots[h], i + 1); return; }  // BTreeMap collect(): last duplicate wins
+        h = (h + 1) & mask;
+    }
+}
+__global__ void m_count_kernel(const Fr *__restrict__ f, const Fr *__restrict__ t, uint32_t usable, const uint32_t *__restrict__ slots,
+                               uint32_t mask, uint32_t *counts, int *err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= usable) return;
+    const Fr key = fp_load(f + i);
+    uint32_t h = key_hash(key) & mask;
+    while (true) {
+        const uint32_t s = slots[h];
+        if (s == 0) { atomicExch(err, 1); return; }  // input not in table: unsatisfied lookup
+        if (fp_load(t + (s - 1)) == key) { atomicAdd(&counts[s - 1], 1u); return; }
+        h = (h + 1) & mask;
+    }
+}
+__global__ void counts_to_fr_kernel(const uint32_t *__restrict__ counts, uint32_t n, Fr *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fp_store(out + i, fp_from_u64<FrParams>(counts[i]));
+}
+
+// ---------------------------------------------------------------------------------------------------------- helpers
+static Fr fr_from_u64(uint64_t v) { return fp_from_u64<FrParams>(v); }
+static bool fr_less(const Fr &a, const Fr &b) {  // halo2curves Ord: canonical integer comparison
+    Fr x = fp_to_canonical(a), y = fp_to_canonical(b);
+    for (int i = 7; i >= 0; --i) {
+        if (x.l[i] != y.l[i]) return x.l[i] < y.l[i];
+    }
+    return false;
+}
+static Fr fr_pow_i64(const Fr &base, const Fr &base_inv, int64_t e) { return e >= 0 ? fp_pow_u64(base, (uint64_t)e) : fp_pow_u64(base_inv, (uint64_t)(-e)); }
+
+struct DevPool {  // owns device allocations of a pk / session
+    std::vector<void *> ptrs;
+    ~DevPool() { for (void *p : ptrs) cudaFree(p); }
+    int32_t alloc(size_t bytes, void **out) {
+        ZKB_CUDA(cudaMalloc(out, bytes ? bytes : 32));
+        ptrs.push_back(*out);
+        return ZKB_OK;
+    }
+    int32_t fr(uint64_t n, Fr **out) { return alloc(n * sizeof(Fr), (void **)out); }
+};
+
+}  // namespace zkb
+using namespace zkb;
+
+struct zkb_pk {
+    zkb_ctx *ctx = nullptr;
+    Csf cs;
+    uint32_t k = 0, ext_k = 0, E = 0, qdeg = 0, chunk = 0, nsets = 0;
+    uint64_t n = 0, N = 0;
+    Fr omega, omega_inv, ext_omega, ext_omega_inv, n_inv, N_inv, zeta;
+    std::vector<Fr> t_inv;
+    DevPool pool;
+    std::vector<Fr *> fixed_values, fixed_polys, sigma_values, sigma_polys;
+    Fr *l0_poly = nullptr, *llast_poly = nullptr, *lblind_poly = nullptr, *xid_poly = nullptr, *omega_pows = nullptr;
+    G1Affine *g = nullptr, *g_lagrange = nullptr;
+};
+
+struct zkb_session {
+    zkb_pk *pk = nullptr;
+    Blake2b tr{"Halo2-Transcript"};
+    std::vector<uint8_t> proof;
+    DevPool pool;
+    std::vector<Fr *> inst_values, inst_polys, adv_values;
+    std::vector<Fr> challenges;
+    uint32_t next_phase = 0;
+    bool finished = false;
+};
+
+namespace zkb {
+
+// ---------------------------------------------------------------------------------------------------------- transcript
+static void tr_common_scalar(zkb_session *s, const Fr &v) {
+    const uint8_t pre = 2;
+    Fr c = fp_to_canonical(v);
+    s->tr.update(&pre, 1);
+    s->tr.update(c.l, 32);
+}
+static void tr_write_scalar(zkb_session *s, const Fr &v) {
+    tr_common_scalar(s, v);
+    Fr c = fp_to_canonical(v);
+    const uint8_t *b = (const uint8_t *)c.l;
+    s->proof.insert(s->proof.end(), b, b + 32);
+}
+static int32_t tr_write_point(zkb_session *s, const G1Affine &p) {
+    if (p.is_identity()) { set_error("cannot write points at infinity to the transcript"); return ZKB_ERR_STATE; }
+    const uint8_t pre = 1;
+    Fq x = fp_to_canonical(p.x), y = fp_to_canonical(p.y);
+    s->tr.update(&pre, 1);
+    s->tr.update(x.l, 32);
+    s->tr.update(y.l, 32);
+    uint8_t comp[32];
+    g1_compress(p, comp);
+    s->proof.insert(s->proof.end(), comp, comp + 32);
+    return ZKB_OK;
+}
+static Fr tr_squeeze(zkb_session *s) {
+    const uint8_t pre = 0;
+    s->tr.update(&pre, 1);
+    uint8_t h[64];
+    s->tr.finalize_copy(h);
+    Fr lo, hi;
+    memcpy(lo.l, h, 32);
+    memcpy(hi.l, h + 32, 32);
+    // Fr::from_uniform_bytes: (lo + hi * 2^256) mod r, computed with Montgomery multiplications by R^2
+    const Fr r2 = Fr::r2();
+    return fp_add(fp_mul(lo, r2), fp_mul(fp_mul(hi, r2), r2));
+}
+
+// ---------------------------------------------------------------------------------------------------------- basis changes
+static int32_t lagrange_to_coeff(zkb_pk *pk, const Fr *values, Fr *poly, cudaStream_t st) {
+    return ntt_fr_device(pk->ctx, values, poly, pk->k, pk->omega_inv, &pk->n_inv, 0, nullptr, st);
+}
+static int32_t commit(zkb_pk *pk, const Fr *scalars, const G1Affine *bases, uint64_t len, G1Affine *out, cudaStream_t st) {
+    return msm_g1_device(pk->ctx, scalars, bases, len, out, st);
+}
+
+// program bundle uploaded to the device
+struct DeviceProgram {
+    Instr *code = nullptr;
+    uint32_t ncode = 0;
+    int nregs = 0;
+    Fr *consts = nullptr;
+};
+static int32_t upload_program(DevPool &pool, const ProgramBuilder &pb, const ExprBuilder &eb, DeviceProgram &dp, cudaStream_t st) {
+    dp.ncode = (uint32_t)pb.code.size();
+    dp.nregs = pb.max_regs_used;
+    ZKB_TRY(pool.alloc(pb.code.size() * sizeof(Instr) + 8, (void **)&dp.code));
+    ZKB_TRY(pool.alloc(eb.consts.size() * sizeof(Fr) + 32, (void **)&dp.consts));
+    ZKB_CUDA(cudaMemcpyAsync(dp.code, pb.code.data(), pb.code.size() * sizeof(Instr), cudaMemcpyHostToDevice, st));
+    ZKB_CUDA(cudaMemcpyAsync(dp.consts, eb.consts.data(), eb.consts.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKB_CUDA(cudaStreamSynchronize(st));  // host vectors may die after return
+    return ZKB_OK;
+}
+template <class T>
+static int32_t upload_table(DevPool &pool, const std::vector<T *> &host, T ***dev, cudaStream_t st) {
+    ZKB_TRY(pool.alloc(host.size() * sizeof(T *) + 8, (void **)dev));
+    ZKB_CUDA(cudaMemcpyAsync(*dev, host.data(), host.size() * sizeof(T *), cudaMemcpyHostToDevice, st));
+    ZKB_CUDA(cudaStreamSynchronize(st));
+    return ZKB_OK;
+}
+
+// translate CSF nodes into ExprBuilder nodes; column slot numbering is supplied by the caller
+struct SlotMap { uint32_t fixed0, advice0, instance0; };
+static uint32_t translate(const Csf &cs, uint32_t node, ExprBuilder &eb, const SlotMap &sm, const std::vector<Fr> &challenges, std::vector<int64_t> &memo) {
+    if (memo[node] >= 0) return (uint32_t)memo[node];
+    const auto &nd = cs.nodes[node];
+    uint32_t r = 0;
+    switch (nd[0]) {
+    case N_CONST: r = eb.constant(cs.consts[nd[1]]); break;
+    case N_FIXED: r = eb.col(sm.fixed0 + nd[1], (int32_t)nd[2]); break;
+    case N_ADVICE: r = eb.col(sm.advice0 + nd[1], (int32_t)nd[2]); break;
+    case N_INSTANCE: r = eb.col(sm.instance0 + nd[1], (int32_t)nd[2]); break;
+    case N_CHALLENGE: r = eb.constant(challenges[nd[1]]); break;
+    case N_NEG: r = eb.neg(translate(cs, nd[1], eb, sm, challenges, memo)); break;
+    case N_ADD: { uint32_t a = translate(cs, nd[1], eb, sm, challenges, memo), b = translate(cs, nd[2], eb, sm, challenges, memo); r = eb.add(a, b); } break;
+    case N_MUL: { uint32_t a = translate(cs, nd[1], eb, sm, challenges, memo), b = translate(cs, nd[2], eb, sm, challenges, memo); r = eb.mul(a, b); } break;
+    case N_SCALED: { uint32_t a = translate(cs, nd[1], eb, sm, challenges, memo); r = eb.mul(a, eb.constant(cs.consts[nd[2]])); } break;
+    }
+    memo[node] = r;
+    return r;
+}
+// compressed = fold(exprs, acc * theta + e), first term taken as is (0 * theta + e0 == e0)
+static uint32_t compress_exprs(const Csf &cs, const std::vector<uint32_t> &exprs, ExprBuilder &eb, const SlotMap &sm, const std::vector<Fr> &ch,
+                               std::vector<int64_t> &memo, const Fr &theta) {
+    uint32_t acc = translate(cs, exprs[0], eb, sm, ch, memo);
+    for (size_t i = 1; i < exprs.size(); ++i) acc = eb.add(eb.mul(acc, eb.constant(theta)), translate(cs, exprs[i], eb, sm, ch, memo));
+    return acc;
+}
+
+}  // namespace zkb
+
+// ================================================================================================ C ABI: proving key
+extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
+                                 const uint64_t *const *sigma_values, const uint64_t *g, const uint64_t *g_lagrange, zkb_pk **out) {
+    ZKB_ARG(ctx && csf && g && g_lagrange && out);
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<zkb_pk> pk(new zkb_pk());
+    pk->ctx = ctx;
+    if (!parse_csf(csf, csf_words, pk->cs)) return ZKB_ERR_ARG;
+    const Csf &cs = pk->cs;
+    ZKB_ARG((cs.nf == 0 || fixed_values) && (cs.perm.empty() || sigma_values));
+    cudaStream_t st = ctx->stream;
+    pk->k = cs.k;
+    pk->n = 1ull << cs.k;
+    const uint64_t n = pk->n;
+    // EvaluationDomain::new(j = cs.degree(), k)
+    pk->qdeg = cs.d - 1;
+    pk->ext_k = cs.k;
+    while ((1ull << pk->ext_k) < n * pk->qdeg) pk->ext_k++;
+    ZKB_ARG(pk->ext_k <= 28);
+    pk->N = 1ull << pk->ext_k;
+    pk->E = (uint32_t)(pk->N / n);
+    pk->chunk = cs.d - 2;
+    pk->nsets = (uint32_t)((cs.perm.size() + pk->chunk - 1) / pk->chunk);
+    pk->ext_omega = host_root_of_unity(pk->ext_k);
+    pk->omega = pk->ext_omega;
+    for (uint32_t i = cs.k; i < pk->ext_k; ++i) pk->omega = fp_sqr(pk->omega);
+    pk->omega_inv = fp_inv(pk->omega);
+    pk->ext_omega_inv = fp_inv(pk->ext_omega);
+    pk->n_inv = fp_inv(fr_from_u64(n));
+    pk->N_inv = fp_inv(fr_from_u64(pk->N));
+    pk->zeta = host_zeta();
+    pk->t_inv.resize(pk->E);
+    for (uint32_t j = 0; j < pk->E; ++j) {
+        Fr gj = fp_mul(pk->zeta, fp_pow_u64(pk->ext_omega, j));
+        pk->t_inv[j] = fp_inv(fp_sub(fp_pow_u64(gj, n), Fr::one()));
+    }
+    // SRS
+    ZKB_TRY(pk->pool.alloc(n * sizeof(G1Affine), (void **)&pk->g));
+    ZKB_TRY(pk->pool.alloc(n * sizeof(G1Affine), (void **)&pk->g_lagrange));
+    ZKB_CUDA(cudaMemcpyAsync(pk->g, g, n * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
+    ZKB_CUDA(cudaMemcpyAsync(pk->g_lagrange, g_lagrange, n * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
+    // fixed / sigma columns: values and coefficient form
+    auto ingest = [&](const uint64_t *const *src, size_t cnt, std::vector<Fr *> &vals, std::vector<Fr *> &polys) -> int32_t {
+        vals.resize(cnt);
+        polys.resize(cnt);
+        for (size_t i = 0; i < cnt; ++i) {
+            ZKB_TRY(pk->pool.fr(n, &vals[i]));
+            ZKB_TRY(pk->pool.fr(n, &polys[i]));
+            ZKB_CUDA(cudaMemcpyAsync(vals[i], src[i], n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            ZKB_TRY(lagrange_to_coeff(pk.get(), vals[i], polys[i], st));
+        }
+        return ZKB_OK;
+    };
+    ZKB_TRY(ingest(fixed_values, cs.nf, pk->fixed_values, pk->fixed_polys));
+    ZKB_TRY(ingest(sigma_values, cs.perm.size(), pk->sigma_values, pk->sigma_polys));
+    // l_0, l_last, l_blind (Lagrange indicator vectors -> coefficient form), X (identity polynomial), omega^i
+    ZKB_TRY(pk->pool.fr(n, &pk->l0_poly));
+    ZKB_TRY(pk->pool.fr(n, &pk->llast_poly));
+    ZKB_TRY(pk->pool.fr(n, &pk->lblind_poly));
+    ZKB_TRY(pk->pool.fr(n, &pk->xid_poly));
+    ZKB_TRY(pk->pool.fr(n, &pk->omega_pows));
+    ZKB_CUDA(cudaMemsetAsync(pk->l0_poly, 0, n * sizeof(Fr), st));
+    ZKB_CUDA(cudaMemsetAsync(pk->llast_poly, 0, n * sizeof(Fr), st));
+    ZKB_CUDA(cudaMemsetAsync(pk->lblind_poly, 0, n * sizeof(Fr), st));
+    ZKB_CUDA(cudaMemsetAsync(pk->xid_poly, 0, n * sizeof(Fr), st));
+    ZKB_ARG(n > cs.bf + 1);
+    set_one_kernel<<<1, 1, 0, st>>>(pk->l0_poly, 0);
+    set_one_kernel<<<1, 1, 0, st>>>(pk->llast_poly, n - cs.bf - 1);
+    fill_range_one_kernel<<<(cs.bf + 127) / 128, 128, 0, st>>>(pk->lblind_poly, n - cs.bf, n);
+    if (n > 1) set_one_kernel<<<1, 1, 0, st>>>(pk->xid_poly, 1);
+    ctx->launches += 4;
+    ZKB_TRY(lagrange_to_coeff(pk.get(), pk->l0_poly, pk->l0_poly, st));
+    ZKB_TRY(lagrange_to_coeff(pk.get(), pk->llast_poly, pk->llast_poly, st));
+    ZKB_TRY(lagrange_to_coeff(pk.get(), pk->lblind_poly, pk->lblind_poly, st));
+    ZKB_TRY(fr_powers_device(ctx, pk->omega, n, pk->omega_pows, st));
+    ZKB_CUDA(cudaStreamSynchronize(st));
+    *out = pk.release();
+    return ZKB_OK;
+}
+
+extern "C" int32_t zkb_pk_destroy(zkb_pk *pk) {
+    if (pk) {
+        cudaSetDevice(pk->ctx->device);
+        cudaStreamSynchronize(pk->ctx->stream);
+        delete pk;
+    }
+    return ZKB_OK;
+}
+
+// ================================================================================================ C ABI: proof session
+extern "C" int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4], const uint64_t *const *instance_values, const uint32_t *instance_lens,
+                                   zkb_session **out) {
+    ZKB_ARG(pk && transcript_repr && out && (pk->cs.ni == 0 || (instance_values && instance_lens)));
+    ZKB_CUDA(cudaSetDevice(pk->ctx->device));
+    std::unique_ptr<zkb_session> s(new zkb_session());
+    s->pk = pk;
+    const Csf &cs = pk->cs;
+    const uint64_t n = pk->n;
+    cudaStream_t st = pk->ctx->stream;
+    Fr repr;
+    memcpy(repr.l, transcript_repr, 32);
+    tr_common_scalar(s.get(), repr);  // vk.hash_into(transcript)
+    s->inst_values.resize(cs.ni);
+    s->inst_polys.resize(cs.ni);
+    for (uint32_t c = 0; c < cs.ni; ++c) {
+        ZKB_ARG(instance_lens[c] <= n - (cs.bf + 1));
+        ZKB_TRY(s->pool.fr(n, &s->inst_values[c]));
+        ZKB_TRY(s->pool.fr(n, &s->inst_polys[c]));
+        ZKB_CUDA(cudaMemsetAsync(s->inst_values[c], 0, n * sizeof(Fr), st));
+        for (uint32_t i = 0; i < instance_lens[c]; ++i) {  // KZG: QUERY_INSTANCE = false -> values are absorbed as scalars
+            Fr v;
+            memcpy(v.l, instance_values[c] + 4 * i, 32);
+            tr_common_scalar(s.get(), v);
+        }
+        if (instance_lens[c]) ZKB_CUDA(cudaMemcpyAsync(s->inst_values[c], instance_values[c], (size_t)instance_lens[c] * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        ZKB_TRY(lagrange_to_coeff(pk, s->inst_values[c], s->inst_polys[c], st));
+    }
+    s->adv_values.assign(cs.na, nullptr);
+    s->challenges.assign(cs.nch, Fr::zero());
+    ZKB_CUDA(cudaStreamSynchronize(st));
+    *out = s.release();
+    return ZKB_OK;
+}
+
+extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const uint64_t *const *advice_columns, uint64_t *challenges_out) {
+    ZKB_ARG(s && advice_columns);
+    zkb_pk *pk = s->pk;
+    const Csf &cs = pk->cs;
+    if (phase != s->next_phase || phase >= cs.nphases || s->finished) { set_error("advice phases must be submitted in order"); return ZKB_ERR_STATE; }
+    ZKB_CUDA(cudaSetDevice(pk->ctx->device));
+    cudaStream_t st = pk->ctx->stream;
+    const uint64_t n = pk->n;
+    for (uint32_t c = 0; c < cs.na; ++c) {
+        if (cs.adv_phase[c] != phase) continue;
+        ZKB_ARG(advice_columns[c] != nullptr);
+        ZKB_TRY(s->pool.fr(n, &s->adv_values[c]));
+        ZKB_CUDA(cudaMemcpyAsync(s->adv_values[c], advice_columns[c], n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        G1Affine cm;
+        ZKB_TRY(commit(pk, s->adv_values[c], pk->g_lagrange, n, &cm, st));
+        ZKB_TRY(tr_write_point(s, cm));
+    }
+    for (uint32_t i = 0; i < cs.nch; ++i) {
+        if (cs.ch_phase[i] == phase) {
+            s->challenges[i] = tr_squeeze(s);
+            if (challenges_out) memcpy(challenges_out + 4 * i, s->challenges[i].l, 32);
+        }
+    }
+    s->next_phase++;
+    return ZKB_OK;
+}
+
+extern "C" int32_t zkb_session_destroy(zkb_session *s) {
+    if (s) {
+        cudaSetDevice(s->pk->ctx->device);
+        cudaStreamSynchronize(s->pk->ctx->stream);
+        delete s;
+    }
+    return ZKB_OK;
+}
+
+namespace zkb {
+
+struct OpenQuery {
+    int poly_id;        // identity of the committed polynomial
+    const Fr *poly;     // device coefficients (n)
+    int64_t rot;        // point = x * omega^rot
+    Fr point;
+    Fr eval;
+};
+
+static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const uint64_t *phi_blinds, const uint64_t *random_poly_host) {
+    zkb_pk *pk = s->pk;
+    zkb_ctx *ctx = pk->ctx;
+    const Csf &cs = pk->cs;
+    const uint64_t n = pk->n;
+    const uint32_t bf = cs.bf, k = cs.k;
+    const uint32_t usable = (uint32_t)(n - bf - 1);
+    cudaStream_t st = ctx->stream;
+    DevPool &pool = s->pool;
+    const size_t nl = cs.lookups.size();
+    const Fr one = Fr::one();
+
+    // ---------------------------------------------------------------- theta; mv-lookup prepare (compress, multiplicities)
+    const Fr theta = tr_squeeze(s);
+    // value-domain column table: [fixed | advice | instance | sigma | omega_pows]
+    const SlotMap vsm{0, cs.nf, cs.nf + cs.na};
+    const uint32_t v_sigma0 = cs.nf + cs.na + cs.ni, v_omega = v_sigma0 + (uint32_t)cs.perm.size();
+    std::vector<Fr *> vcols;
+    for (auto p : pk->fixed_values) vcols.push_back(p);
+    for (auto p : s->adv_values) vcols.push_back(p);
+    for (auto p : s->inst_values) vcols.push_back(p);
+    for (auto p : pk->sigma_values) vcols.push_back(p);
+    vcols.push_back(pk->omega_pows);
+    Fr **d_vcols = nullptr;
+    ZKB_TRY(upload_table(pool, vcols, &d_vcols, st));
+
+    std::vector<std::vector<Fr *>> lk_f(nl);   // compressed inputs per lookup / input set
+    std::vector<Fr *> lk_t(nl), lk_m(nl);
+    for (size_t l = 0; l < nl; ++l) {
+        const CsfLookup &lk = cs.lookups[l];
+        ExprBuilder eb;
+        ProgramBuilder pb(eb);
+        std::vector<int64_t> memo(cs.nodes.size(), -1);
+        std::vector<ProgramBuilder::Root> roots;
+        std::vector<Fr *> outs;
+        for (size_t j = 0; j < lk.inputs.size(); ++j) {
+            Fr *a;
+            ZKB_TRY(pool.fr(n, &a));
+            lk_f[l].push_back(a);
+            outs.push_back(a);
+            roots.push_back({compress_exprs(cs, lk.inputs[j], eb, vsm, s->challenges, memo, theta), ProgramBuilder::STORE, (uint32_t)j});
+        }
+        ZKB_TRY(pool.fr(n, &lk_t[l]));
+        outs.push_back(lk_t[l]);
+        roots.push_back({compress_exprs(cs, lk.table, eb, vsm, s->challenges, memo, theta), ProgramBuilder::STORE, (uint32_t)lk.inputs.size()});
+        if (!pb.scope(roots)) { set_error("lookup %zu: %s", l, pb.error.c_str()); return ZKB_ERR_ARG; }
+        DeviceProgram dp;
+        ZKB_TRY(upload_program(pool, pb, eb, dp, st));
+        Fr **d_outs = nullptr;
+        ZKB_TRY(upload_table(pool, outs, &d_outs, st));
+        ZKB_TRY(expr_run_device(ctx, dp.code, dp.ncode, dp.nregs, d_vcols, dp.consts, d_outs, k, 1, 0, st));
+        // multiplicities over the usable rows
+        uint32_t tsize = 1;
+        while (tsize < 2 * usable) tsize <<= 1;
+        uint32_t *slots = nullptr, *counts = nullptr;
+        int *d_err = nullptr;
+        ZKB_TRY(pool.alloc((size_t)tsize * 4, (void **)&slots));
+        ZKB_TRY(pool.alloc((size_t)n * 4 + 16, (void **)&counts));
+        d_err = (int *)(counts + n);
+        ZKB_CUDA(cudaMemsetAsync(slots, 0, (size_t)tsize * 4, st));
+        ZKB_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 4 + 16, st));
+        const unsigned ub = (usable + 255) / 256;
+        m_insert_kernel<<<ub, 256, 0, st>>>(lk_t[l], usable, slots, tsize - 1);
+        for (size_t j = 0; j < lk.inputs.size(); ++j) m_count_kernel<<<ub, 256, 0, st>>>(lk_f[l][j], lk_t[l], usable, slots, tsize - 1, counts, d_err);
+        ZKB_TRY(pool.fr(n, &lk_m[l]));
+        counts_to_fr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts, (uint32_t)n, lk_m[l]);
+        ctx->launches += 2 + lk.inputs.size();
+        int herr = 0;
+        ZKB_CUDA(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
+        ZKB_CUDA(cudaStreamSynchronize(st));
+        if (herr) { set_error("lookup %zu: an input row is not in the table (unsatisfied witness)", l); return ZKB_ERR_ARG; }
+        G1Affine cm;
+        ZKB_TRY(commit(pk, lk_m[l], pk->g_lagrange, n, &cm, st));
+        ZKB_TRY(tr_write_point(s, cm));
+    }
+
+    // ---------------------------------------------------------------- beta, gamma; permutation grand products
+    const Fr beta = tr_squeeze(s);
+    const Fr gamma = tr_squeeze(s);
+    auto perm_slot_values = [&](const std::array<uint32_t, 2> &c) -> uint32_t {
+        return c[0] == N_FIXED ? vsm.fixed0 + c[1] : c[0] == N_ADVICE ? vsm.advice0 + c[1] : vsm.instance0 + c[1];
+    };
+    std::vector<Fr *> zs(pk->nsets);
+    {
+        Fr last_z = one;
+        Fr delta_pow = one;
+        Fr delta;
+        {   // DELTA = 7^(2^28)
+            Fr seven = fr_from_u64(7);
+            delta = seven;
+            for (int i = 0; i < 28; ++i) delta = fp_sqr(delta);
+        }
+        Fr *num, *den, *tmp;
+        ZKB_TRY(pool.fr(n, &num));
+        ZKB_TRY(pool.fr(n, &den));
+        ZKB_TRY(pool.fr(n, &tmp));
+        for (uint32_t si = 0; si < pk->nsets; ++si) {
+            ExprBuilder eb;
+            ProgramBuilder pb(eb);
+            uint32_t nnum = 0, nden = 0;
+            bool first = true;
+            for (uint32_t j = si * pk->chunk; j < std::min<size_t>((si + 1) * pk->chunk, cs.perm.size()); ++j) {
+                const uint32_t v = eb.col(perm_slot_values(cs.perm[j]), 0);
+                const uint32_t dterm = eb.add(eb.add(v, eb.mul(eb.col(v_sigma0 + j, 0), eb.constant(beta))), eb.constant(gamma));
+                const uint32_t nterm = eb.add(eb.add(v, eb.mul(eb.col(v_omega, 0), eb.constant(fp_mul(beta, delta_pow)))), eb.constant(gamma));
+                nden = first ? dterm : eb.mul(nden, dterm);
+                nnum = first ? nterm : eb.mul(nnum, nterm);
+                first = false;
+                delta_pow = fp_mul(delta_pow, delta);
+            }
+            if (!pb.scope({{nnum, ProgramBuilder::STORE, 0}, {nden, ProgramBuilder::STORE, 1}})) { set_error("permutation: %s", pb.error.c_str()); return ZKB_ERR_ARG; }
+            DeviceProgram dp;
+            ZKB_TRY(upload_program(pool, pb, eb, dp, st));
+            std::vector<Fr *> outs{num, den};
+            Fr **d_outs = nullptr;
+            ZKB_TRY(upload_table(pool, outs, &d_outs, st));
+            ZKB_TRY(expr_run_device(ctx, dp.code, dp.ncode, dp.nregs, d_vcols, dp.consts, d_outs, k, 1, 0, st));
+            ZKB_TRY(batch_invert_device(ctx, den, tmp, n, st));
+            mul_arrays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, tmp, den, n);  // den <- modified values
+            ctx->launches++;
+            ZKB_TRY(pool.fr(n, &zs[si]));
+            ZKB_TRY(prefix_product_device(ctx, den, n, last_z, zs[si], st));
+            ZKB_CUDA(cudaMemcpyAsync(zs[si] + (n - bf), z_blinds + 4ull * bf * si, (size_t)bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            ZKB_CUDA(cudaMemcpyAsync(&last_z, zs[si] + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            ZKB_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    for (uint32_t si = 0; si < pk->nsets; ++si) {
+        G1Affine cm;
+        ZKB_TRY(commit(pk, zs[si], pk->g_lagrange, n, &cm, st));
+        ZKB_TRY(tr_write_point(s, cm));
+    }
+
+    // ---------------------------------------------------------------- lookup grand sums phi
+    std::vector<Fr *> phis(nl);
+    for (size_t l = 0; l < nl; ++l) {
+        const size_t J = lk_f[l].size();
+        // denominators (f_j + beta), (t + beta) into one contiguous array, inverted at once
+        Fr *dens, *invs, *dterm;
+        ZKB_TRY(pool.fr((J + 1) * n, &dens));
+        ZKB_TRY(pool.fr((J + 1) * n, &invs));
+        ZKB_TRY(pool.fr(n, &dterm));
+        std::vector<Fr *> cols;
+        for (auto p : lk_f[l]) cols.push_back(p);
+        cols.push_back(lk_t[l]);          // slot J
+        cols.push_back(lk_m[l]);          // slot J + 1
+        for (size_t j = 0; j <= J; ++j) cols.push_back(invs + j * n);  // slots J + 2 ..
+        Fr **d_cols = nullptr;
+        ZKB_TRY(upload_table(pool, cols, &d_cols, st));
+        {
+            ExprBuilder eb;
+            ProgramBuilder pb(eb);
+            std::vector<ProgramBuilder::Root> roots;
+            std::vector<Fr *> outs;
+            for (size_t j = 0; j <= J; ++j) {
+                roots.push_back({eb.add(eb.col((uint32_t)j, 0), eb.constant(beta)), ProgramBuilder::STORE, (uint32_t)j});
+                outs.push_back(dens + j * n);
+            }
+            if (!pb.scope(roots)) { set_error("lookup sum: %s", pb.error.c_str()); return ZKB_ERR_ARG; }
+            DeviceProgram dp;
+            ZKB_TRY(upload_program(pool, pb, eb, dp, st));
+            Fr **d_outs = nullptr;
+            ZKB_TRY(upload_table(pool, outs, &d_outs, st));
+            ZKB_TRY(expr_run_device(ctx, dp.code, dp.ncode, dp.nregs, d_cols, dp.consts, d_outs, k, 1, 0, st));
+        }
+        ZKB_TRY(batch_invert_device(ctx, dens, invs, (J + 1) * n, st));
+        {
+            ExprBuilder eb;
+            ProgramBuilder pb(eb);
+            uint32_t acc = eb.neg(eb.mul(eb.col((uint32_t)J + 1, 0), eb.col((uint32_t)(J + 2 + J), 0)));  // - m / (t + beta)
+            for (size_t j = 0; j < J; ++j) acc = eb.add(acc, eb.col((uint32_t)(J + 2 + j), 0));
+            if (!pb.scope({{acc, ProgramBuilder::STORE, 0}})) { set_error("lookup sum: %s", pb.error.c_str()); return ZKB_ERR_ARG; }
+            DeviceProgram dp;
+            ZKB_TRY(upload_program(pool, pb, eb, dp, st));
+            std::vector<Fr *> outs{dterm};
+            Fr **d_outs = nullptr;
+            ZKB_TRY(upload_table(pool, outs, &d_outs, st));
+            ZKB_TRY(expr_run_device(ctx, dp.code, dp.ncode, dp.nregs, d_cols, dp.consts, d_outs, k, 1, 0, st));
+        }
+        ZKB_TRY(pool.fr(n, &phis[l]));
+        ZKB_TRY(prefix_sum_device(ctx, dterm, n, Fr::zero(), phis[l], st));
+        ZKB_CUDA(cudaMemcpyAsync(phis[l] + (n - bf), phi_blinds + 4ull * bf * l, (size_t)bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    }
+    for (size_t l = 0; l < nl; ++l) {
+        G1Affine cm;
+        ZKB_TRY(commit(pk, phis[l], pk->g_lagrange, n, &cm, st));
+        ZKB_TRY(tr_write_point(s, cm));
+    }
+
+    // ---------------------------------------------------------------- vanishing: random polynomial
+    Fr *random_poly;
+    ZKB_TRY(pool.fr(n, &random_poly));
+    ZKB_CUDA(cudaMemcpyAsync(random_poly, random_poly_host, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    {
+        G1Affine cm;
+        ZKB_TRY(commit(pk, random_poly, pk->g, n, &cm, st));
+        ZKB_TRY(tr_write_point(s, cm));
+    }
+    const Fr y = tr_squeeze(s);
+
+    // ---------------------------------------------------------------- coefficient forms
+    auto to_coeff_new = [&](const std::vector<Fr *> &vals, std::vector<Fr *> &polys) -> int32_t {
+        polys.resize(vals.size());
+        for (size_t i = 0; i < vals.size(); ++i) {
+            ZKB_TRY(pool.fr(n, &polys[i]));
+            ZKB_TRY(lagrange_to_coeff(pk, vals[i], polys[i], st));
+        }
+        return ZKB_OK;
+    };
+    std::vector<Fr *> adv_polys, z_polys, phi_polys, m_polys;
+    ZKB_TRY(to_coeff_new(s->adv_values, adv_polys));
+    ZKB_TRY(to_coeff_new(zs, z_polys));
+    ZKB_TRY(to_coeff_new(phis, phi_polys));
+    ZKB_TRY(to_coeff_new(lk_m, m_polys));
+
+    // ---------------------------------------------------------------- quotient numerator program (plonk/evaluation.rs order)
+    // coset-domain slot table: [fixed | advice | instance | sigma | z | phi | m | l0 | l_last | l_blind | X]
+    std::vector<Fr *> qpolys;
+    for (auto p : pk->fixed_polys) qpolys.push_back(p);
+    for (auto p : adv_polys) qpolys.push_back(p);
+    for (auto p : s->inst_polys) qpolys.push_back(p);
+    const uint32_t q_sigma0 = (uint32_t)qpolys.size();
+    for (auto p : pk->sigma_polys) qpolys.push_back(p);
+    const uint32_t q_z0 = (uint32_t)qpolys.size();
+    for (auto p : z_polys) qpolys.push_back(p);
+    const uint32_t q_phi0 = (uint32_t)qpolys.size();
+    for (auto p : phi_polys) qpolys.push_back(p);
+    const uint32_t q_m0 = (uint32_t)qpolys.size();
+    for (auto p : m_polys) qpolys.push_back(p);
+    const uint32_t q_l0 = (uint32_t)qpolys.size();
+    qpolys.push_back(pk->l0_poly);
+    qpolys.push_back(pk->llast_poly);
+    qpolys.push_back(pk->lblind_poly);
+    qpolys.push_back(pk->xid_poly);
+    const uint32_t q_llast = q_l0 + 1, q_lblind = q_l0 + 2, q_x = q_l0 + 3;
+    ZKB_ARG(qpolys.size() < 65536);
+    const SlotMap qsm{0, cs.nf, cs.nf + cs.na};
+
+    ExprBuilder qeb;
+    ProgramBuilder qpb(qeb);
+    const uint32_t y_idx = qeb.const_slot(y);
+    {
+        std::vector<int64_t> memo(cs.nodes.size(), -1);
+        for (uint32_t gnode : cs.gates) {
+            if (!qpb.scope({{translate(cs, gnode, qeb, qsm, s->challenges, memo), ProgramBuilder::HORNER, y_idx}})) { set_error("gate: %s", qpb.error.c_str()); return ZKB_ERR_ARG; }
+        }
+        auto lactive = [&]() { return qeb.sub(qeb.sub(qeb.constant(one), qeb.col(q_llast, 0)), qeb.col(q_lblind, 0)); };
+        if (pk->nsets) {
+            const uint32_t z0 = qeb.col(q_z0, 0), zl = qeb.col(q_z0 + pk->nsets - 1, 0);
+            if (!qpb.scope({{qeb.mul(qeb.sub(qeb.constant(one), z0), qeb.col(q_l0, 0)), ProgramBuilder::HORNER, y_idx}})) return ZKB_ERR_ARG;
+            if (!qpb.scope({{qeb.mul(qeb.sub(qeb.mul(zl, zl), zl), qeb.col(q_llast, 0)), ProgramBuilder::HORNER, y_idx}})) return ZKB_ERR_ARG;
+            for (uint32_t i = 1; i < pk->nsets; ++i) {
+                const uint32_t t = qeb.mul(qeb.sub(qeb.col(q_z0 + i, 0), qeb.col(q_z0 + i - 1, -(int32_t)(bf + 1))), qeb.col(q_l0, 0));
+                if (!qpb.scope({{t, ProgramBuilder::HORNER, y_idx}})) return ZKB_ERR_ARG;
+            }
+            Fr delta_pow = one, delta;
+            {
+                Fr seven = fr_from_u64(7);
+                delta = seven;
+                for (int i = 0; i < 28; ++i) delta = fp_sqr(delta);
+            }
+            for (uint32_t si = 0; si < pk->nsets; ++si) {
+                uint32_t left = qeb.col(q_z0 + si, 1), right = qeb.col(q_z0 + si, 0);
+                for (uint32_t j = si * pk->chunk; j < std::min<size_t>((si + 1) * pk->chunk, cs.perm.size()); ++j) {
+                    const auto &c = cs.perm[j];
+                    const uint32_t vslot = c[0] == N_FIXED ? qsm.fixed0 + c[1] : c[0] == N_ADVICE ? qsm.advice0 + c[1] : qsm.instance0 + c[1];
+                    const uint32_t v = qeb.col(vslot, 0);
+                    left = qeb.mul(left, qeb.add(qeb.add(v, qeb.mul(qeb.col(q_sigma0 + j, 0), qeb.constant(beta))), qeb.constant(gamma)));
+                    right = qeb.mul(right, qeb.add(qeb.add(v, qeb.mul(qeb.col(q_x, 0), qeb.constant(fp_mul(beta, delta_pow)))), qeb.constant(gamma)));
+                    delta_pow = fp_mul(delta_pow, delta);
+                }
+                if (!qpb.scope({{qeb.mul(qeb.sub(left, right), lactive()), ProgramBuilder::HORNER, y_idx}})) { set_error("permutation: %s", qpb.error.c_str()); return ZKB_ERR_ARG; }
+            }
+        }
+        for (size_t l = 0; l < nl; ++l) {
+            const CsfLookup &lk = cs.lookups[l];
+            std::vector<uint32_t> fsb;
+            for (auto &inp : lk.inputs) fsb.push_back(qeb.add(compress_exprs(cs, inp, qeb, qsm, s->challenges, memo, theta), qeb.constant(beta)));
+            const uint32_t tb = qeb.add(compress_exprs(cs, lk.table, qeb, qsm, s->challenges, memo, theta), qeb.constant(beta));
+            uint32_t prod = fsb[0];
+            for (size_t j = 1; j < fsb.size(); ++j) prod = qeb.mul(prod, fsb[j]);
+            uint32_t ssum = 0;
+            bool have_sum = false;
+            for (size_t i = 0; i < fsb.size(); ++i) {
+                uint32_t pr = 0;
+                bool have = false;
+                for (size_t j = 0; j < fsb.size(); ++j) {
+                    if (j == i) continue;
+                    pr = have ? qeb.mul(pr, fsb[j]) : fsb[j];
+                    have = true;
+                }
+                if (!have) pr = qeb.constant(one);
+                ssum = have_sum ? qeb.add(ssum, pr) : pr;
+                have_sum = true;
+            }
+            const uint32_t phi = qeb.col(q_phi0 + (uint32_t)l, 0), phi_next = qeb.col(q_phi0 + (uint32_t)l, 1), m = qeb.col(q_m0 + (uint32_t)l, 0);
+            const uint32_t lhs = qeb.mul(qeb.mul(tb, prod), qeb.sub(phi_next, phi));
+            const uint32_t rhs = qeb.sub(qeb.mul(tb, ssum), qeb.mul(m, prod));
+            std::vector<ProgramBuilder::Root> roots = {{qeb.mul(phi, qeb.col(q_l0, 0)), ProgramBuilder::HORNER, y_idx},
+                                                       {qeb.mul(phi, qeb.col(q_llast, 0)), ProgramBuilder::HORNER, y_idx},
+                                                       {qeb.mul(qeb.sub(lhs, rhs), lactive()), ProgramBuilder::HORNER, y_idx}};
+            if (!qpb.scope(roots)) { set_error("lookup %zu: %s", l, qpb.error.c_str()); return ZKB_ERR_ARG; }
+        }
+    }
+    // one STOREACC per coset part (the scale constant differs): emit them as separate tiny programs appended at launch
+    std::vector<uint32_t> tinv_idx(pk->E);
+    for (uint32_t j = 0; j < pk->E; ++j) tinv_idx[j] = qeb.const_slot(pk->t_inv[j]);
+    const size_t base_len = qpb.code.size();
+    DeviceProgram qdp;
+    {
+        // device code buffer holds the common body + one trailing STOREACC slot that is rewritten per part
+        qpb.store_acc(0, tinv_idx[0]);
+        ZKB_TRY(upload_program(pool, qpb, qeb, qdp, st));
+    }
+
+    // ---------------------------------------------------------------- evaluate h on the extended domain, part by part
+    Fr *slab, *pows, *h_ext;
+    ZKB_TRY(pool.fr(qpolys.size() * n, &slab));
+    ZKB_TRY(pool.fr(n, &pows));
+    ZKB_TRY(pool.fr(pk->N, &h_ext));
+    std::vector<Fr *> qcols(qpolys.size());
+    for (size_t i = 0; i < qpolys.size(); ++i) qcols[i] = slab + i * n;
+    Fr **d_qcols = nullptr, **d_hout = nullptr;
+    ZKB_TRY(upload_table(pool, qcols, &d_qcols, st));
+    std::vector<Fr *> hout{h_ext};
+    ZKB_TRY(upload_table(pool, hout, &d_hout, st));
+    for (uint32_t j = 0; j < pk->E; ++j) {
+        const Fr gj = fp_mul(pk->zeta, fp_pow_u64(pk->ext_omega, j));
+        ZKB_TRY(fr_powers_device(ctx, gj, n, pows, st));
+        for (size_t i = 0; i < qpolys.size(); ++i) ZKB_TRY(ntt_fr_device(ctx, qpolys[i], qcols[i], k, pk->omega, nullptr, 0, pows, st));
+        Instr tail{OP_STOREACC, 0, 0, 0, 0u | (tinv_idx[j] << 8)};
+        ZKB_CUDA(cudaMemcpyAsync(qdp.code + base_len, &tail, sizeof(Instr), cudaMemcpyHostToDevice, st));
+        ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, pk->E, j, st));
+        ZKB_CUDA(cudaStreamSynchronize(st));  // `tail` lives on the stack
+    }
+    // extended_to_coeff: inverse NTT over the extended domain, 1/N, undo the zeta coset, keep n*(d-1) coefficients
+    ZKB_TRY(ntt_fr_device(ctx, h_ext, h_ext, pk->ext_k, pk->ext_omega_inv, &pk->N_inv, 2, nullptr, st));
+    for (uint32_t i = 0; i < pk->qdeg; ++i) {
+        G1Affine cm;
+        ZKB_TRY(commit(pk, h_ext + (size_t)i * n, pk->g, n, &cm, st));
+        ZKB_TRY(tr_write_point(s, cm));
+    }
+    const Fr x = tr_squeeze(s);
+    const Fr xn = fp_pow_u64(x, n);
+
+    // ---------------------------------------------------------------- evaluations (prover.rs order)
+    // h(X) = sum_i x^(n i) piece_i
+    Fr *h_poly;
+    ZKB_TRY(pool.fr(n, &h_poly));
+    {
+        std::vector<Fr *> pcs;
+        std::vector<Fr> cf;
+        Fr cur = one;
+        for (uint32_t i = 0; i < pk->qdeg; ++i) { pcs.push_back(h_ext + (size_t)i * n); cf.push_back(cur); cur = fp_mul(cur, xn); }
+        Fr **d_p = nullptr;
+        Fr *d_c = nullptr;
+        ZKB_TRY(upload_table(pool, pcs, &d_p, st));
+        ZKB_TRY(pool.fr(cf.size(), &d_c));
+        ZKB_CUDA(cudaMemcpyAsync(d_c, cf.data(), cf.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        ZKB_TRY(lincomb_device(ctx, d_p, d_c, (uint32_t)pcs.size(), n, h_poly, false, st));
+        ZKB_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<OpenQuery> queries;
+    int next_id = 0;
+    std::vector<int> adv_id(cs.na), fix_id(cs.nf), sig_id(cs.perm.size()), z_id(pk->nsets), phi_id(nl), m_id(nl);
+    for (auto &v : adv_id) v = next_id++;
+    for (auto &v : fix_id) v = next_id++;
+    for (auto &v : sig_id) v = next_id++;
+    for (auto &v : z_id) v = next_id++;
+    for (auto &v : phi_id) v = next_id++;
+    for (auto &v : m_id) v = next_id++;
+    const int h_id = next_id++, rand_id = next_id++;
+    const int64_t rot_last = -(int64_t)(bf + 1);
+    // (1) the evaluations written to the transcript, in order; `queries` is built afterwards in the multiopen order
+    struct EvalReq { int poly_id; const Fr *poly; int64_t rot; };
+    std::vector<EvalReq> reqs;
+    for (auto &q : cs.advq) reqs.push_back({adv_id[q[0]], adv_polys[q[0]], q[1]});
+    for (auto &q : cs.fixq) reqs.push_back({fix_id[q[0]], pk->fixed_polys[q[0]], q[1]});
+    reqs.push_back({rand_id, random_poly, 0});
+    for (size_t i = 0; i < cs.perm.size(); ++i) reqs.push_back({sig_id[i], pk->sigma_polys[i], 0});
+    for (uint32_t i = 0; i < pk->nsets; ++i) {
+        reqs.push_back({z_id[i], z_polys[i], 0});
+        reqs.push_back({z_id[i], z_polys[i], 1});
+        if (i + 1 != pk->nsets) reqs.push_back({z_id[i], z_polys[i], rot_last});
+    }
+    for (size_t l = 0; l < nl; ++l) {
+        reqs.push_back({phi_id[l], phi_polys[l], 0});
+        reqs.push_back({phi_id[l], phi_polys[l], 1});
+        reqs.push_back({m_id[l], m_polys[l], 0});
+    }
+    const size_t n_written = reqs.size();
+    reqs.push_back({h_id, h_poly, 0});  // needed by SHPLONK, not written
+    // batch by rotation
+    std::map<int64_t, std::vector<size_t>> by_rot;
+    for (size_t i = 0; i < reqs.size(); ++i) by_rot[reqs[i].rot].push_back(i);
+    std::vector<Fr> evals(reqs.size());
+    std::map<int64_t, Fr> point_of;
+    for (auto &kv : by_rot) {
+        const Fr pt = fp_mul(x, fr_pow_i64(pk->omega, pk->omega_inv, kv.first));
+        point_of[kv.first] = pt;
+        std::vector<Fr *> ptrs;
+        for (size_t i : kv.second) ptrs.push_back(const_cast<Fr *>(reqs[i].poly));
+        Fr **d_p = nullptr;
+        ZKB_TRY(upload_table(pool, ptrs, &d_p, st));
+        std::vector<Fr> res(ptrs.size());
+        ZKB_TRY(poly_eval_device(ctx, d_p, (uint32_t)ptrs.size(), n, pt, res.data(), st));
+        for (size_t t = 0; t < kv.second.size(); ++t) evals[kv.second[t]] = res[t];
+    }
+    for (size_t i = 0; i < n_written; ++i) tr_write_scalar(s, evals[i]);
+    std::map<std::pair<int, int64_t>, Fr> eval_of;
+    for (size_t i = 0; i < reqs.size(); ++i) eval_of[{reqs[i].poly_id, reqs[i].rot}] = evals[i];
+
+    // (2) multiopen queries in prover.rs order
+    auto push_q = [&](int id, const Fr *poly, int64_t rot) { queries.push_back({id, poly, rot, point_of[rot], eval_of[{id, rot}]}); };
+    for (auto &q : cs.advq) push_q(adv_id[q[0]], adv_polys[q[0]], q[1]);
+    for (uint32_t i = 0; i < pk->nsets; ++i) { push_q(z_id[i], z_polys[i], 0); push_q(z_id[i], z_polys[i], 1); }
+    for (int i = (int)pk->nsets - 2; i >= 0; --i) push_q(z_id[i], z_polys[i], rot_last);
+    for (size_t l = 0; l < nl; ++l) { push_q(phi_id[l], phi_polys[l], 0); push_q(phi_id[l], phi_polys[l], 1); push_q(m_id[l], m_polys[l], 0); }
+    for (auto &q : cs.fixq) push_q(fix_id[q[0]], pk->fixed_polys[q[0]], q[1]);
+    for (size_t i = 0; i < cs.perm.size(); ++i) push_q(sig_id[i], pk->sigma_polys[i], 0);
+    push_q(h_id, h_poly, 0);
+    push_q(rand_id, random_poly, 0);
+
+    // ---------------------------------------------------------------- SHPLONK (multiopen/shplonk/prover.rs)
+    const Fr sy = tr_squeeze(s);
+    // construct_intermediate_sets
+    struct Commit { int id; const Fr *poly; std::vector<int64_t> rots; };
+    std::vector<Commit> cmap;
+    std::vector<int64_t> super_rots;
+    for (auto &q : queries) {
+        if (std::find(super_rots.begin(), super_rots.end(), q.rot) == super_rots.end()) super_rots.push_back(q.rot);
+        auto it = std::find_if(cmap.begin(), cmap.end(), [&](const Commit &c) { return c.id == q.poly_id; });
+        if (it == cmap.end()) cmap.push_back({q.poly_id, q.poly, {q.rot}});
+        else if (std::find(it->rots.begin(), it->rots.end(), q.rot) == it->rots.end()) it->rots.push_back(q.rot);
+    }
+    auto sort_rots = [&](std::vector<int64_t> &r) { std::sort(r.begin(), r.end(), [&](int64_t a, int64_t b) { return fr_less(point_of[a], point_of[b]); }); };
+    sort_rots(super_rots);
+    for (auto &c : cmap) sort_rots(c.rots);
+    struct RSet { std::vector<int64_t> rots; std::vector<Commit *> comms; };
+    std::vector<RSet> rsets;
+    for (auto &c : cmap) {
+        auto it = std::find_if(rsets.begin(), rsets.end(), [&](const RSet &r) { return r.rots == c.rots; });
+        if (it == rsets.end()) rsets.push_back({c.rots, {&c}});
+        else it->comms.push_back(&c);
+    }
+    const Fr sv = tr_squeeze(s);
+    // low-degree interpolant through (points, evals): coefficients, low to high
+    auto interpolate = [&](const std::vector<Fr> &pts, const std::vector<Fr> &evs) {
+        const size_t m = pts.size();
+        std::vector<Fr> coeffs(m, Fr::zero());
+        for (size_t j = 0; j < m; ++j) {
+            std::vector<Fr> num{one};
+            Fr den = one;
+            for (size_t t = 0; t < m; ++t) {
+                if (t == j) continue;
+                std::vector<Fr> nx(num.size() + 1, Fr::zero());
+                for (size_t i = 0; i < num.size(); ++i) {
+                    nx[i + 1] = fp_add(nx[i + 1], num[i]);
+                    nx[i] = fp_sub(nx[i], fp_mul(pts[t], num[i]));
+                }
+                num.swap(nx);
+                den = fp_mul(den, fp_sub(pts[j], pts[t]));
+            }
+            const Fr sc = fp_mul(evs[j], fp_inv(den));
+            for (size_t i = 0; i < m; ++i) coeffs[i] = fp_add(coeffs[i], fp_mul(num[i], sc));
+        }
+        return coeffs;
+    };
+    auto horner_host = [&](const std::vector<Fr> &c, const Fr &at) {
+        Fr acc = Fr::zero();
+        for (size_t i = c.size(); i-- > 0;) acc = fp_add(fp_mul(acc, at), c[i]);
+        return acc;
+    };
+    Fr *hx, *work, *work2, *d_small;
+    ZKB_TRY(pool.fr(n, &hx));
+    ZKB_TRY(pool.fr(n, &work));
+    ZKB_TRY(pool.fr(n, &work2));
+    ZKB_TRY(pool.fr(64, &d_small));
+    ZKB_CUDA(cudaMemsetAsync(hx, 0, n * sizeof(Fr), st));
+    struct SetData { std::vector<Fr> pts; std::vector<std::vector<Fr>> r_coeffs; };
+    std::vector<SetData> sdata(rsets.size());
+    {
+        Fr vpow = one;
+        for (size_t si = 0; si < rsets.size(); ++si) {
+            RSet &rs = rsets[si];
+            SetData &sd = sdata[si];
+            for (int64_t r : rs.rots) sd.pts.push_back(point_of[r]);
+            ZKB_ARG(sd.pts.size() <= 32);
+            // N_i(X) = sum_j y^j (P_ij(X) - R_ij(X))
+            std::vector<Fr *> ptrs;
+            std::vector<Fr> cf;
+            std::vector<Fr> rsum(sd.pts.size(), Fr::zero());
+            Fr ypow = one;
+            for (Commit *c : rs.comms) {
+                std::vector<Fr> evs;
+                for (int64_t r : rs.rots) evs.push_back(eval_of[{c->id, r}]);
+                sd.r_coeffs.push_back(interpolate(sd.pts, evs));
+                for (size_t i = 0; i < sd.pts.size(); ++i) rsum[i] = fp_add(rsum[i], fp_mul(sd.r_coeffs.back()[i], ypow));
+                ptrs.push_back(const_cast<Fr *>(c->poly));
+                cf.push_back(ypow);
+                ypow = fp_mul(ypow, sy);
+            }
+            Fr **d_p = nullptr;
+            Fr *d_c = nullptr;
+            ZKB_TRY(upload_table(pool, ptrs, &d_p, st));
+            ZKB_TRY(pool.fr(cf.size(), &d_c));
+            ZKB_CUDA(cudaMemcpyAsync(d_c, cf.data(), cf.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            ZKB_TRY(lincomb_device(ctx, d_p, d_c, (uint32_t)ptrs.size(), n, work, false, st));
+            ZKB_CUDA(cudaMemcpyAsync(d_small, rsum.data(), rsum.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            sub_low_kernel<<<1, 32, 0, st>>>(work, d_small, (uint32_t)rsum.size());
+            ctx->launches++;
+            ZKB_CUDA(cudaStreamSynchronize(st));
+            // divide by the vanishing polynomial of the set, one root at a time
+            Fr *src = work, *dst = work2;
+            for (const Fr &p : sd.pts) {
+                ZKB_TRY(kate_division_device(ctx, src, n, p, dst, st));
+                std::swap(src, dst);
+            }
+            // h_x += v^i * Q_i
+            std::vector<Fr *> one_ptr{src};
+            Fr **d_q = nullptr;
+            Fr *d_v = nullptr;
+            ZKB_TRY(upload_table(pool, one_ptr, &d_q, st));
+            ZKB_TRY(pool.fr(1, &d_v));
+            ZKB_CUDA(cudaMemcpyAsync(d_v, &vpow, sizeof(Fr), cudaMemcpyHostToDevice, st));
+            ZKB_TRY(lincomb_device(ctx, d_q, d_v, 1, n, hx, true, st));
+            ZKB_CUDA(cudaStreamSynchronize(st));
+            vpow = fp_mul(vpow, sv);
+        }
+    }
+    {
+        G1Affine cm;
+        ZKB_TRY(commit(pk, hx, pk->g, n, &cm, st));
+        ZKB_TRY(tr_write_point(s, cm));
+    }
+    const Fr su = tr_squeeze(s);
+    {
+        // L(X) = sum_i v^i z_i sum_j y^j (P_ij(X) - r_ij) - zt * h_x(X), scaled by 1/z_0, divided by (X - u)
+        std::vector<Fr> super_pts;
+        for (int64_t r : super_rots) super_pts.push_back(point_of[r]);
+        std::vector<Fr> zdiff(rsets.size());
+        for (size_t si = 0; si < rsets.size(); ++si) {
+            Fr z = one;
+            for (size_t t = 0; t < super_rots.size(); ++t) {
+                if (std::find(rsets[si].rots.begin(), rsets[si].rots.end(), super_rots[t]) == rsets[si].rots.end()) z = fp_mul(z, fp_sub(su, super_pts[t]));
+            }
+            zdiff[si] = z;
+        }
+        Fr zt = one;
+        for (auto &p : super_pts) zt = fp_mul(zt, fp_sub(su, p));
+        const Fr z0inv = fp_inv(zdiff[0]);
+        std::vector<Fr *> ptrs;
+        std::vector<Fr> cf;
+        Fr const_term = Fr::zero();
+        Fr vpow = one;
+        for (size_t si = 0; si < rsets.size(); ++si) {
+            Fr ypow = one;
+            for (size_t ci = 0; ci < rsets[si].comms.size(); ++ci) {
+                const Fr w = fp_mul(fp_mul(fp_mul(vpow, zdiff[si]), ypow), z0inv);
+                ptrs.push_back(const_cast<Fr *>(rsets[si].comms[ci]->poly));
+                cf.push_back(w);
+                const_term = fp_add(const_term, fp_mul(w, horner_host(sdata[si].r_coeffs[ci], su)));
+                ypow = fp_mul(ypow, sy);
+            }
+            vpow = fp_mul(vpow, sv);
+        }
+        ptrs.push_back(hx);
+        cf.push_back(fp_neg(fp_mul(zt, z0inv)));
+        Fr **d_p = nullptr;
+        Fr *d_c = nullptr;
+        ZKB_TRY(upload_table(pool, ptrs, &d_p, st));
+        ZKB_TRY(pool.fr(cf.size(), &d_c));
+        ZKB_CUDA(cudaMemcpyAsync(d_c, cf.data(), cf.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        ZKB_TRY(lincomb_device(ctx, d_p, d_c, (uint32_t)ptrs.size(), n, work, false, st));
+        ZKB_CUDA(cudaMemcpyAsync(d_small, &const_term, sizeof(Fr), cudaMemcpyHostToDevice, st));
+        sub_low_kernel<<<1, 32, 0, st>>>(work, d_small, 1);
+        ctx->launches++;
+        ZKB_CUDA(cudaStreamSynchronize(st));
+        ZKB_TRY(kate_division_device(ctx, work, n, su, work2, st));
+        G1Affine cm;
+        ZKB_TRY(commit(pk, work2, pk->g, n, &cm, st));
+        ZKB_TRY(tr_write_point(s, cm));
+    }
+    s->finished = true;
+    return ZKB_OK;
+}
+
+}  // namespace zkb
+
+extern "C" int32_t zkb_prove_finish(zkb_session *s, const uint64_t *z_blinds, const uint64_t *phi_blinds, const uint64_t *random_poly,
+                                    uint8_t *proof_out, uint64_t proof_cap, uint64_t *proof_len) {
+    ZKB_ARG(s && random_poly && proof_len);
+    zkb_pk *pk = s->pk;
+    if (s->next_phase != pk->cs.nphases || s->finished) { set_error("zkb_prove_finish: advice phases incomplete or session already finished"); return ZKB_ERR_STATE; }
+    ZKB_ARG((pk->nsets == 0 || z_blinds) && (pk->cs.lookups.empty() || phi_blinds));
+    ZKB_CUDA(cudaSetDevice(pk->ctx->device));
+    ZKB_TRY(prove_finish_impl(s, z_blinds, phi_blinds, random_poly));
+    *proof_len = s->proof.size();
+    if (proof_out) {
+        ZKB_ARG(proof_cap >= s->proof.size());
+        memcpy(proof_out, s->proof.data(), s->proof.size());
+    }
+    return ZKB_OK;
+}
