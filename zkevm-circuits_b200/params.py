@@ -1,0 +1,73 @@
+"""Host mirror of halo2_proofs::poly::kzg::commitment::ParamsKZG<Bn256> (the prover-side fields) built on the GPU.
+
+`unsafe_setup_with_s` follows ParamsKZG::unsafe_setup_with_s (used by the reference at
+zkevm-circuits/src/super_circuit/test.rs:74): g[i] = [s^i] G1, g_lagrange[i] = [L_i(s)] G1 with
+L_i(s) = w^i (s^n - 1) / (n (s - w^i)).  All arithmetic runs through the CUDA kernels (no CPU field code here).
+"""
+import numpy as np
+
+from . import arithmetic as A
+from . import poly
+
+
+def fr_scalar_dev(v, device="cuda"):
+    """python int -> 1-element device tensor holding the Montgomery form (conversion done by the device kernel)."""
+    import torch
+    limbs = [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+    t = torch.from_numpy(np.array([limbs], dtype=np.uint64).view(np.int64)).to(device)
+    return A.field_unop_dev(A.FR, A.UOP_TO_MONT, t)
+
+
+def fr_ints_to_dev(vals_int64, device="cuda"):
+    """int64 tensor of small non-negative values (n,) -> (n,4) Montgomery tensor."""
+    import torch
+    z = torch.zeros((vals_int64.shape[0], 4), dtype=torch.int64, device=device)
+    z[:, 0] = vals_int64
+    return A.field_unop_dev(A.FR, A.UOP_TO_MONT, z)
+
+
+def bcast(scalar_t, n):
+    return scalar_t.expand(n, 4).contiguous()
+
+
+def fr_pow2k_dev(t, k):
+    for _ in range(k):
+        t = A.field_unop_dev(A.FR, A.UOP_SQR, t)
+    return t
+
+
+def g1_generator():
+    import torch
+    g_can = torch.tensor([[1, 0, 0, 0], [2, 0, 0, 0]], dtype=torch.int64, device="cuda")
+    return A.field_unop_dev(A.FQ, A.UOP_TO_MONT, g_can).cpu().numpy().view(np.uint64).reshape(8)
+
+
+class ParamsKZG:
+    def __init__(self, k, g, g_lagrange):
+        self.k, self.n = k, 1 << k
+        self.g, self.g_lagrange = g, g_lagrange          # device tensors (n, 8)
+
+    @staticmethod
+    def unsafe_setup_with_s(k, s):
+        n = 1 << k
+        gen = g1_generator()
+        s_t = fr_scalar_dev(s)
+        s_host = s_t.cpu().numpy().view(np.uint64)[0]
+        pw = poly.fr_powers_dev(s_host, n)
+        g = A.g1_fixed_base_mul_dev(gen, pw)
+        omega, _ = A.root_of_unity(k)
+        W = poly.fr_powers_dev(omega, n)
+        den = A.field_binop_dev(A.FR, A.OP_SUB, bcast(s_t, n), W)
+        inv = A.fr_batch_invert_dev(den)
+        one = fr_scalar_dev(1)
+        c1 = A.field_binop_dev(A.FR, A.OP_MUL, A.field_binop_dev(A.FR, A.OP_SUB, fr_pow2k_dev(s_t, k), one),
+                               A.field_unop_dev(A.FR, A.UOP_INV, fr_scalar_dev(n)))
+        L = A.field_binop_dev(A.FR, A.OP_MUL, A.field_binop_dev(A.FR, A.OP_MUL, W, inv), bcast(c1, n))
+        gl = A.g1_fixed_base_mul_dev(gen, L)
+        return ParamsKZG(k, g, gl)
+
+    def commit_lagrange(self, values_dev):
+        return A.best_multiexp_dev(values_dev, self.g_lagrange)
+
+    def commit(self, coeffs_dev):
+        return A.best_multiexp_dev(coeffs_dev, self.g[: coeffs_dev.shape[0]].contiguous())
