@@ -294,22 +294,35 @@ FF_HD Fp<PR> fp_mul(const Fp<PR> &a, const Fp<PR> &b) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) r.l[i] = borrow ? r.l[i] : t.l[i];
 #else
-    // portable CIOS (host)
-    uint32_t t[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < 8; ++i) {
-        uint64_t c = 0;
-        for (int j = 0; j < 8; ++j) { c += (uint64_t)a.l[j] * b.l[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
-        c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
-        uint32_t m = t[0] * PR::INV;
-        c = (uint64_t)m * PR::P(0) + t[0]; c >>= 32;
-        for (int j = 1; j < 8; ++j) { c += (uint64_t)m * PR::P(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
-        c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+    // host: CIOS on 4 x 64-bit limbs with unsigned __int128 (same layout: limb pairs of the 32-bit view)
+    uint64_t A[4], B[4], P64[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        A[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+        B[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
+        P64[i] = (uint64_t)PR::P(2 * i) | ((uint64_t)PR::P(2 * i + 1) << 32);
     }
-    int64_t br = 0;
-    uint32_t u[8];
-    for (int i = 0; i < 8; ++i) { int64_t d = (int64_t)t[i] - PR::P(i) + br; u[i] = (uint32_t)d; br = d >> 32; }
-    bool ge = t[8] != 0 || br == 0;
-    for (int i = 0; i < 8; ++i) r.l[i] = ge ? u[i] : t[i];
+    // -p^{-1} mod 2^64 from the 32-bit constant by one Newton step: inv64 = inv32 * (2 + p0 * inv32)   (signs: INV = -p^{-1})
+    uint64_t inv64 = PR::INV;
+    inv64 = inv64 * (2 + P64[0] * inv64);
+    typedef unsigned __int128 u128;
+    for (int i = 0; i < 4; ++i) {
+        u128 c = 0;
+        for (int j = 0; j < 4; ++j) { c += (u128)A[j] * B[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+        const uint64_t m = t[0] * inv64;
+        c = (u128)m * P64[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 4; ++j) { c += (u128)m * P64[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    uint64_t u[4];
+    u128 br = 0;
+    for (int i = 0; i < 4; ++i) { u128 d = (u128)t[i] - P64[i] - (uint64_t)br; u[i] = (uint64_t)d; br = (d >> 64) & 1; }
+    const bool ge = t[4] != 0 || br == 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t v = ge ? u[i] : t[i];
+        r.l[2 * i] = (uint32_t)v;
+        r.l[2 * i + 1] = (uint32_t)(v >> 32);
+    }
 #endif
     return r;
 }

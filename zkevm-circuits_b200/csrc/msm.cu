@@ -37,7 +37,7 @@ static MsmCfg choose_cfg(uint64_t n) {
     m.c = (uint32_t)c;
     m.windows = (255 + m.c - 1) / m.c;
     m.half = 1u << (m.c - 1);
-    m.seg_log = m.c - 1 > 7 ? 7 : m.c - 1;
+    m.seg_log = 0;
     return m;
 }
 
@@ -146,13 +146,49 @@ static void exclusive_scan_u32(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, 
     ctx->launches += 3;
 }
 
-// ---- bucket accumulation: one thread per bucket -------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__restrict__ bases, const uint32_t *__restrict__ offsets,
-                                                            const uint32_t *__restrict__ sorted, G1Xyzz *__restrict__ buckets,
-                                                            uint32_t nbuckets) {
+// ---- bucket accumulation: balanced tasks of at most ACC_CH entries ---------------------------------------------------
+// Witness columns are highly structured (most scalars are 0, 1 or small), so bucket sizes are wildly skewed: a bucket is
+// cut into ceil(len / ACC_CH) tasks; level 0 adds affine bases gathered through the sorted index list, the following levels
+// add the XYZZ partials of the previous level, until every bucket holds one value.  Task -> bucket by binary search in the
+// exclusive scan of per-bucket task counts.
+constexpr uint32_t ACC_CH = 64;
+
+__global__ void task_count_kernel(const uint32_t *__restrict__ seg_off, uint32_t nseg, uint32_t *__restrict__ tcount) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbuckets) return;
-    const uint32_t beg = offsets[b], end = offsets[b + 1];
+    if (b >= nseg) return;
+    const uint32_t len = seg_off[b + 1] - seg_off[b];
+    tcount[b] = (len + ACC_CH - 1) / ACC_CH;
+}
+__global__ void max_u32_kernel(const uint32_t *__restrict__ off, uint32_t nseg, uint32_t *__restrict__ out) {
+    uint32_t m = 0;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nseg; b += gridDim.x * blockDim.x) {
+        const uint32_t len = off[b + 1] - off[b];
+        m = len > m ? len : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t y = __shfl_down_sync(0xffffffffu, m, o);
+        m = y > m ? y : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+__device__ __forceinline__ uint32_t find_segment(const uint32_t *__restrict__ toff, uint32_t nseg, uint32_t t) {
+    // largest b with toff[b] <= t   (toff has nseg + 1 entries, non-decreasing)
+    uint32_t lo = 0, hi = nseg;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (toff[mid] <= t) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(128) msm_acc_level0_kernel(const G1Affine *__restrict__ bases, const uint32_t *__restrict__ seg_off,
+                                                            const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ toff,
+                                                            uint32_t nseg, uint32_t ntasks, G1Xyzz *__restrict__ part) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntasks) return;
+    const uint32_t b = find_segment(toff, nseg, t);
+    const uint32_t beg = seg_off[b] + (t - toff[b]) * ACC_CH;
+    const uint32_t lim = seg_off[b + 1];
+    const uint32_t end = beg + ACC_CH < lim ? beg + ACC_CH : lim;
     G1Xyzz acc = G1Xyzz::identity();
     for (uint32_t k = beg; k < end; ++k) {
         const uint32_t e = sorted[k];
@@ -160,38 +196,54 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__r
         if (e >> 31) p = g1_neg(p);
         g1_add_mixed(acc, p);
     }
-    g1_store_xyzz(buckets + b, acc);
+    g1_store_xyzz(part + t, acc);
+}
+__global__ void __launch_bounds__(128) msm_acc_levelN_kernel(const G1Xyzz *__restrict__ in, const uint32_t *__restrict__ seg_off,
+                                                            const uint32_t *__restrict__ toff, uint32_t nseg, uint32_t ntasks,
+                                                            G1Xyzz *__restrict__ part) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntasks) return;
+    const uint32_t b = find_segment(toff, nseg, t);
+    const uint32_t beg = seg_off[b] + (t - toff[b]) * ACC_CH;
+    const uint32_t lim = seg_off[b + 1];
+    const uint32_t end = beg + ACC_CH < lim ? beg + ACC_CH : lim;
+    G1Xyzz acc = g1_load_xyzz(in + beg);
+    for (uint32_t k = beg + 1; k < end; ++k) g1_add(acc, g1_load_xyzz(in + k));
+    g1_store_xyzz(part + t, acc);
+}
+// buckets[b] = the single remaining partial of segment b (or the identity for an empty bucket)
+__global__ void msm_gather_buckets_kernel(const G1Xyzz *__restrict__ part, const uint32_t *__restrict__ seg_off, uint32_t nseg,
+                                          G1Xyzz *__restrict__ buckets) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nseg) return;
+    const uint32_t beg = seg_off[b], end = seg_off[b + 1];
+    g1_store_xyzz(buckets + b, end > beg ? g1_load_xyzz(part + beg) : G1Xyzz::identity());
 }
 
-// ---- window reduction, stage 1: segment running sums ---------------------------------------------------------
-// thread (w, seg): buckets j in [seg*L, (seg+1)*L) of window w (bucket j has weight j+1)
-//   partial = sum_j (j + 1) * B_j = sum_j (j - seg*L + 1) * B_j + (seg*L) * sum_j B_j
-__global__ void __launch_bounds__(128) msm_segment_kernel(const G1Xyzz *__restrict__ buckets, G1Xyzz *__restrict__ partials, MsmCfg m) {
-    const uint32_t segs = m.half >> m.seg_log;
+// ---- window reduction: sum_j j * in[j] (0-based weights) by levels of length-L running sums ----------------------------
+// level kernel, thread (w, s): segment s of window w (count entries per window):
+//   acc_out = sum_{j=1}^{len-1} j * in[s*L + j],   run_out = sum_j in[s*L + j]
+// so  sum_j j*in[j] = sum_s acc_s + L * sum_s s * run_s  -> recurse on the `run` array; no per-thread scalar multiplication.
+__global__ void __launch_bounds__(128) msm_wsum_level_kernel(const G1Xyzz *__restrict__ in, uint32_t count, uint32_t log_l, uint32_t windows,
+                                                            G1Xyzz *__restrict__ acc_out, G1Xyzz *__restrict__ run_out) {
+    const uint32_t L = 1u << log_l;
+    const uint32_t segs = (count + L - 1) >> log_l;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m.windows * segs) return;
-    const uint32_t w = t / segs, seg = t % segs;
-    const uint32_t L = 1u << m.seg_log;
-    const G1Xyzz *bk = buckets + (size_t)w * m.half + (size_t)seg * L;
+    if (t >= windows * segs) return;
+    const uint32_t w = t / segs, s = t % segs;
+    const uint32_t base = s << log_l;
+    const uint32_t len = count - base < L ? count - base : L;
+    const G1Xyzz *p = in + (size_t)w * count + base;
     G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity();
-    for (int j = (int)L - 1; j >= 0; --j) {
-        g1_add(running, g1_load_xyzz(bk + j));
+    for (int j = (int)len - 1; j >= 1; --j) {
+        g1_add(running, g1_load_xyzz(p + j));
         g1_add(acc, running);
     }
-    // acc += (seg * L) * running   (double-and-add, MSB first)
-    const uint32_t k = seg * L;
-    if (k) {
-        G1Xyzz r = G1Xyzz::identity();
-        for (int bit = 31 - __clz(k); bit >= 0; --bit) {
-            r = g1_dbl(r);
-            if ((k >> bit) & 1) g1_add(r, running);
-        }
-        g1_add(acc, r);
-    }
-    g1_store_xyzz(partials + t, acc);
+    g1_add(running, g1_load_xyzz(p));
+    g1_store_xyzz(acc_out + t, acc);
+    g1_store_xyzz(run_out + t, running);
 }
-
-// ---- window reduction, stage 2: tree-sum the segment partials of one window (one block per window) -----------
+// plain sums of `segs` entries per window (one block per window); result ADDED into / written to out[w]
 __global__ void __launch_bounds__(256) msm_window_sum_kernel(const G1Xyzz *__restrict__ partials, G1Xyzz *__restrict__ window_sums, uint32_t segs) {
     extern __shared__ uint4 sm4[];
     G1Xyzz *sm = reinterpret_cast<G1Xyzz *>(sm4);
@@ -209,6 +261,19 @@ __global__ void __launch_bounds__(256) msm_window_sum_kernel(const G1Xyzz *__res
         __syncthreads();
     }
     if (threadIdx.x == 0) g1_store_xyzz(window_sums + w, sm[0]);
+}
+// per window: result = S_all + T0, T0 = S(acc_1) + 2^l (S(acc_2) + 2^l (S(acc_3) + ...)); level sums laid out [level][window]
+__global__ void msm_window_combine_kernel(const G1Xyzz *__restrict__ level_sums, const G1Xyzz *__restrict__ all_sum, uint32_t nlevels,
+                                          uint32_t log_l, uint32_t windows, G1Xyzz *__restrict__ out) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= windows) return;
+    G1Xyzz r = g1_load_xyzz(level_sums + (size_t)(nlevels - 1) * windows + w);
+    for (int lv = (int)nlevels - 2; lv >= 0; --lv) {
+        for (uint32_t d = 0; d < log_l; ++d) r = g1_dbl(r);
+        g1_add(r, g1_load_xyzz(level_sums + (size_t)lv * windows + w));
+    }
+    g1_add(r, g1_load_xyzz(all_sum + w));
+    g1_store_xyzz(out + w, r);
 }
 
 // ---- fixed-base scalar multiplication: out[i] = [s_i] base (affine) ------------------------------------------
@@ -235,41 +300,107 @@ int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, ui
     }
     const MsmCfg m = choose_cfg(n);
     const uint32_t nbuckets = m.windows * m.half;
-    const uint32_t segs = m.half >> m.seg_log;
     const uint64_t pairs = n * m.windows;
     ZKB_ARG(pairs < (1ull << 32));
+    const uint32_t log_l = 5;  // window-reduction segment length 32
 
-    // scratch layout A: counts | offsets(+1) | cursors | scan tmp ; B: sorted ; C: buckets | partials | window sums
-    const size_t cnt_bytes = align_up((size_t)(nbuckets + 1) * 4, 256);
+    // scratch A: counts | offsets(+1) | cursors | tcount | toffA(+1) | toffB(+1) | scan tmp | max
+    const size_t cnt_bytes = align_up((size_t)(nbuckets + 2) * 4, 256);
     const size_t tmp_bytes = align_up(((size_t)nbuckets / SCAN_BLK + 2) * 4, 256);
     uint8_t *A = nullptr, *B = nullptr, *C = nullptr;
-    ZKB_TRY(scratch_get(ctx, SCR_MSM_A, 3 * cnt_bytes + tmp_bytes, (void **)&A));
+    ZKB_TRY(scratch_get(ctx, SCR_MSM_A, 6 * cnt_bytes + tmp_bytes + 256, (void **)&A));
     ZKB_TRY(scratch_get(ctx, SCR_MSM_B, pairs * 4, (void **)&B));
-    const size_t bucket_bytes = (size_t)nbuckets * sizeof(G1Xyzz), part_bytes = (size_t)m.windows * segs * sizeof(G1Xyzz);
-    ZKB_TRY(scratch_get(ctx, SCR_MSM_C, bucket_bytes + part_bytes + m.windows * sizeof(G1Xyzz), (void **)&C));
     uint32_t *counts = (uint32_t *)A, *offsets = (uint32_t *)(A + cnt_bytes), *cursors = (uint32_t *)(A + 2 * cnt_bytes);
-    uint32_t *scan_tmp = (uint32_t *)(A + 3 * cnt_bytes);
+    uint32_t *tcount = (uint32_t *)(A + 3 * cnt_bytes), *toff[2] = {(uint32_t *)(A + 4 * cnt_bytes), (uint32_t *)(A + 5 * cnt_bytes)};
+    uint32_t *scan_tmp = (uint32_t *)(A + 6 * cnt_bytes), *d_max = (uint32_t *)(A + 6 * cnt_bytes + tmp_bytes);
     uint32_t *sorted = (uint32_t *)B;
-    G1Xyzz *buckets = (G1Xyzz *)C, *partials = (G1Xyzz *)(C + bucket_bytes), *wsums = (G1Xyzz *)(C + bucket_bytes + part_bytes);
 
     ZKB_CUDA(cudaMemsetAsync(counts, 0, cnt_bytes, st));
-    const unsigned tb = 256, gb = (unsigned)((n + tb - 1) / tb);
+    ZKB_CUDA(cudaMemsetAsync(d_max, 0, 4, st));
+    const unsigned tb = 256, gb = (unsigned)((n + tb - 1) / tb), bb = (nbuckets + 255) / 256;
     msm_digits_kernel<0><<<gb, tb, 0, st>>>(scalars, n, m, counts, nullptr, nullptr);
     exclusive_scan_u32(ctx, counts, offsets, nbuckets, scan_tmp, st);
     ZKB_CUDA(cudaMemcpyAsync(cursors, offsets, (size_t)nbuckets * 4, cudaMemcpyDeviceToDevice, st));
     msm_digits_kernel<1><<<gb, tb, 0, st>>>(scalars, n, m, nullptr, cursors, sorted);
-    msm_accumulate_kernel<<<(nbuckets + 127) / 128, 128, 0, st>>>(bases, offsets, sorted, buckets, nbuckets);
-    msm_segment_kernel<<<(m.windows * segs + 127) / 128, 128, 0, st>>>(buckets, partials, m);
-    uint32_t wt = 32;
-    while (wt < segs && wt < 256) wt <<= 1;
-    msm_window_sum_kernel<<<m.windows, wt, wt * sizeof(G1Xyzz), st>>>(partials, wsums, segs);
-    ctx->launches += 5;
+    max_u32_kernel<<<64, 256, 0, st>>>(offsets, nbuckets, d_max);
+    task_count_kernel<<<bb, 256, 0, st>>>(offsets, nbuckets, tcount);
+    exclusive_scan_u32(ctx, tcount, toff[0], nbuckets, scan_tmp, st);
+    ctx->launches += 4;
+    uint32_t h_info[2] = {0, 0};  // total pairs, level-0 tasks
+    uint32_t h_max = 0;
+    ZKB_CUDA(cudaMemcpyAsync(&h_info[0], offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaMemcpyAsync(&h_info[1], toff[0] + nbuckets, 4, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t total_pairs = h_info[0];
+    uint32_t ntasks = h_info[1];
+
+    // scratch C: part0 | part1 | buckets | level arrays (acc / run per level) | level sums | all-sum | window results
+    const uint32_t half = m.half;
+    uint32_t nlevels = 0, cnt = half;
+    size_t level_entries = 0;
+    while (cnt > 1) { cnt = (cnt + (1u << log_l) - 1) >> log_l; level_entries += 2ull * cnt * m.windows; nlevels++; }
+    if (nlevels == 0) { nlevels = 1; level_entries = 2ull * m.windows; }  // half == 1: one trivial level
+    const size_t part0_n = ntasks ? ntasks : 1, part1_n = (ntasks + ACC_CH - 1) / ACC_CH + nbuckets + 1;
+    const size_t c_entries = part0_n + part1_n + nbuckets + level_entries + (size_t)nlevels * m.windows + 2ull * m.windows;
+    ZKB_TRY(scratch_get(ctx, SCR_MSM_C, c_entries * sizeof(G1Xyzz), (void **)&C));
+    G1Xyzz *part[2] = {(G1Xyzz *)C, (G1Xyzz *)C + part0_n};
+    G1Xyzz *buckets = part[1] + part1_n, *lvl = buckets + nbuckets, *lvl_sums = lvl + level_entries, *all_sum = lvl_sums + (size_t)nlevels * m.windows,
+           *wres = all_sum + m.windows;
+
+    uint64_t extra_adds = 0;
+    if (ntasks) msm_acc_level0_kernel<<<(ntasks + 127) / 128, 128, 0, st>>>(bases, offsets, sorted, toff[0], nbuckets, ntasks, part[0]);
+    ctx->launches++;
+    // further levels while some bucket still holds more than one partial
+    int cur = 0;
+    uint32_t maxlen = (h_max + ACC_CH - 1) / ACC_CH;  // partials per bucket after level 0
+    const uint32_t *seg_off = toff[0];
+    while (maxlen > 1) {
+        const int nxt = cur ^ 1;
+        task_count_kernel<<<bb, 256, 0, st>>>(seg_off, nbuckets, tcount);
+        exclusive_scan_u32(ctx, tcount, toff[nxt], nbuckets, scan_tmp, st);
+        uint32_t nt = 0;
+        ZKB_CUDA(cudaMemcpyAsync(&nt, toff[nxt] + nbuckets, 4, cudaMemcpyDeviceToHost, st));
+        ZKB_CUDA(cudaStreamSynchronize(st));
+        msm_acc_levelN_kernel<<<(nt + 127) / 128, 128, 0, st>>>(part[cur], seg_off, toff[nxt], nbuckets, nt, part[nxt]);
+        ctx->launches += 2;
+        extra_adds += ntasks;
+        ntasks = nt;
+        seg_off = toff[nxt];
+        cur = nxt;
+        maxlen = (maxlen + ACC_CH - 1) / ACC_CH;
+    }
+    msm_gather_buckets_kernel<<<bb, 256, 0, st>>>(part[cur], seg_off, nbuckets, buckets);
+    ctx->launches++;
+
+    // window reduction by levels
+    {
+        const G1Xyzz *in = buckets;
+        uint32_t count = half;
+        G1Xyzz *p = lvl;
+        for (uint32_t lv = 0; lv < nlevels; ++lv) {
+            const uint32_t segs = (count + (1u << log_l) - 1) >> log_l;
+            G1Xyzz *acc_out = p, *run_out = p + (size_t)segs * m.windows;
+            msm_wsum_level_kernel<<<(m.windows * segs + 127) / 128, 128, 0, st>>>(in, count, log_l, m.windows, acc_out, run_out);
+            uint32_t wt = 32;
+            while (wt < segs && wt < 256) wt <<= 1;
+            msm_window_sum_kernel<<<m.windows, wt, wt * sizeof(G1Xyzz), st>>>(acc_out, lvl_sums + (size_t)lv * m.windows, segs);
+            ctx->launches += 2;
+            in = run_out;
+            count = segs;
+            p += 2ull * segs * m.windows;
+            if (lv + 1 == nlevels) {
+                // count == 1 now: run_out[w] is the sum of all buckets of window w
+                ZKB_CUDA(cudaMemcpyAsync(all_sum, run_out, (size_t)m.windows * sizeof(G1Xyzz), cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        msm_window_combine_kernel<<<(m.windows + 31) / 32, 32, 0, st>>>(lvl_sums, all_sum, nlevels, log_l, m.windows, wres);
+        ctx->launches++;
+    }
     ZKB_CUDA(cudaGetLastError());
 
     std::vector<G1Xyzz> h(m.windows);
-    uint32_t total_pairs = 0;
-    ZKB_CUDA(cudaMemcpyAsync(h.data(), wsums, m.windows * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
-    ZKB_CUDA(cudaMemcpyAsync(&total_pairs, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaMemcpyAsync(h.data(), wres, m.windows * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
     ZKB_CUDA(cudaStreamSynchronize(st));
     // Horner over windows on the host (W * c doublings + W additions of single points)
     G1Xyzz acc = h[m.windows - 1];
@@ -278,7 +409,7 @@ int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, ui
         g1_add(acc, h[w]);
     }
     *out_affine_host = g1_to_affine(acc);
-    ctx->msm_last_adds = (uint64_t)total_pairs + 2ull * nbuckets + (uint64_t)m.windows * segs;
+    ctx->msm_last_adds = (uint64_t)total_pairs + extra_adds + 2ull * nbuckets;
     return ZKB_OK;
 }
 

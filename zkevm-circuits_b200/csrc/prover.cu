@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <memory>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 namespace zkb {
 
@@ -113,29 +115,38 @@ __device__ __forceinline__ uint32_t key_hash(const Fr &k) {
     return h;
 }
 __global__ void m_insert_kernel(const Fr *__restrict__ t, uint32_t usable, uint32_t *slots, uint32_t mask) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= usable) return;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= usable) return;
+    const uint32_t i = usable - 1 - tid;  // descending row order: the winning (last) duplicate tends to arrive first
     const Fr key = fp_load(t + i);
     uint32_t h = key_hash(key) & mask;
     while (true) {
         const uint32_t s = atomicCAS(&slots[h], 0u, i + 1);
         if (s == 0) return;
-        if (fp_load(t + (s - 1)) == key) { atomicMax(&slots[h], i + 1); return; }  // BTreeMap collect(): last duplicate wins
+        if (fp_load(t + (s - 1)) == key) {   // BTreeMap collect(): the last duplicate table row wins
+            if (s < i + 1) atomicMax(&slots[h], i + 1);
+            return;
+        }
         h = (h + 1) & mask;
     }
 }
 __global__ void m_count_kernel(const Fr *__restrict__ f, const Fr *__restrict__ t, uint32_t usable, const uint32_t *__restrict__ slots,
                                uint32_t mask, uint32_t *counts, int *err) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= usable) return;
-    const Fr key = fp_load(f + i);
-    uint32_t h = key_hash(key) & mask;
-    while (true) {
-        const uint32_t s = slots[h];
-        if (s == 0) { atomicExch(err, 1); return; }  // input not in table: unsatisfied lookup
-        if (fp_load(t + (s - 1)) == key) { atomicAdd(&counts[s - 1], 1u); return; }
-        h = (h + 1) & mask;
+    uint32_t target = 0xffffffffu;
+    if (i < usable) {
+        const Fr key = fp_load(f + i);
+        uint32_t h = key_hash(key) & mask;
+        while (true) {
+            const uint32_t s = slots[h];
+            if (s == 0) { atomicExch(err, 1); break; }  // input not in table: unsatisfied lookup
+            if (fp_load(t + (s - 1)) == key) { target = s - 1; break; }
+            h = (h + 1) & mask;
+        }
     }
+    // most rows of a zkEVM lookup hit the same few table rows (selector off -> the all-zero row): aggregate per warp
+    const uint32_t peers = __match_any_sync(0xffffffffu, target);
+    if (target != 0xffffffffu && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&counts[target], (uint32_t)__popc(peers));
 }
 __global__ void counts_to_fr_kernel(const uint32_t *__restrict__ counts, uint32_t n, Fr *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,6 +467,30 @@ extern "C" int32_t zkb_session_destroy(zkb_session *s) {
 
 namespace zkb {
 
+// stage timing (ZKB_TRACE=1): wall clock per create_proof stage after a stream synchronise, printed to stderr
+struct StageTrace {
+    bool on;
+    cudaStream_t st;
+    double t0;
+    explicit StageTrace(cudaStream_t s) : st(s) {
+        const char *e = getenv("ZKB_TRACE");
+        on = e && e[0] == '1';
+        t0 = now();
+    }
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    void mark(const char *name) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const double t = now();
+        fprintf(stderr, "[zkb trace] %-28s %9.3f ms\n", name, (t - t0) * 1e3);
+        t0 = t;
+    }
+};
+
 struct OpenQuery {
     int poly_id;        // identity of the committed polynomial
     const Fr *poly;     // device coefficients (n)
@@ -477,6 +512,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     const Fr one = Fr::one();
 
     // ---------------------------------------------------------------- theta; mv-lookup prepare (compress, multiplicities)
+    StageTrace trace(st);
     const Fr theta = tr_squeeze(s);
     // value-domain column table: [fixed | advice | instance | sigma | omega_pows]
     const SlotMap vsm{0, cs.nf, cs.nf + cs.na};
@@ -540,6 +576,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(tr_write_point(s, cm));
     }
 
+    trace.mark("lookups: compress + m + commit");
     // ---------------------------------------------------------------- beta, gamma; permutation grand products
     const Fr beta = tr_squeeze(s);
     const Fr gamma = tr_squeeze(s);
@@ -597,6 +634,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(tr_write_point(s, cm));
     }
 
+    trace.mark("permutation z + commit");
     // ---------------------------------------------------------------- lookup grand sums phi
     std::vector<Fr *> phis(nl);
     for (size_t l = 0; l < nl; ++l) {
@@ -653,6 +691,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(tr_write_point(s, cm));
     }
 
+    trace.mark("lookup phi + commit");
     // ---------------------------------------------------------------- vanishing: random polynomial
     Fr *random_poly;
     ZKB_TRY(pool.fr(n, &random_poly));
@@ -664,6 +703,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     }
     const Fr y = tr_squeeze(s);
 
+    trace.mark("random poly commit");
     // ---------------------------------------------------------------- coefficient forms
     auto to_coeff_new = [&](const std::vector<Fr *> &vals, std::vector<Fr *> &polys) -> int32_t {
         polys.resize(vals.size());
@@ -679,6 +719,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     ZKB_TRY(to_coeff_new(phis, phi_polys));
     ZKB_TRY(to_coeff_new(lk_m, m_polys));
 
+    trace.mark("lagrange_to_coeff (all columns)");
     // ---------------------------------------------------------------- quotient numerator program (plonk/evaluation.rs order)
     // coset-domain slot table: [fixed | advice | instance | sigma | z | phi | m | l0 | l_last | l_blind | X]
     std::vector<Fr *> qpolys;
@@ -779,6 +820,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(upload_program(pool, qpb, qeb, qdp, st));
     }
 
+    trace.mark("quotient program build+upload");
     // ---------------------------------------------------------------- evaluate h on the extended domain, part by part
     Fr *slab, *pows, *h_ext;
     ZKB_TRY(pool.fr(qpolys.size() * n, &slab));
@@ -799,6 +841,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, pk->E, j, st));
         ZKB_CUDA(cudaStreamSynchronize(st));  // `tail` lives on the stack
     }
+    trace.mark("quotient: coset NTTs + fused eval");
     // extended_to_coeff: inverse NTT over the extended domain, 1/N, undo the zeta coset, keep n*(d-1) coefficients
     ZKB_TRY(ntt_fr_device(ctx, h_ext, h_ext, pk->ext_k, pk->ext_omega_inv, &pk->N_inv, 2, nullptr, st));
     for (uint32_t i = 0; i < pk->qdeg; ++i) {
@@ -809,6 +852,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     const Fr x = tr_squeeze(s);
     const Fr xn = fp_pow_u64(x, n);
 
+    trace.mark("extended iNTT + h commits");
     // ---------------------------------------------------------------- evaluations (prover.rs order)
     // h(X) = sum_i x^(n i) piece_i
     Fr *h_poly;
@@ -887,6 +931,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     push_q(h_id, h_poly, 0);
     push_q(rand_id, random_poly, 0);
 
+    trace.mark("evaluations");
     // ---------------------------------------------------------------- SHPLONK (multiopen/shplonk/prover.rs)
     const Fr sy = tr_squeeze(s);
     // construct_intermediate_sets
@@ -1047,6 +1092,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(commit(pk, work2, pk->g, n, &cm, st));
         ZKB_TRY(tr_write_point(s, cm));
     }
+    trace.mark("shplonk");
     s->finished = true;
     return ZKB_OK;
 }
