@@ -83,6 +83,10 @@ ZKB_API int32_t zkb_msm_g1_host(zkb_ctx *ctx, const uint64_t *scalars_host, cons
                         uint64_t out_affine[8], uint64_t *out_jacobian, uint8_t *out_compressed);
 ZKB_API int32_t zkb_msm_g1_dev(zkb_ctx *ctx, const uint64_t *scalars_dev, const uint64_t *bases_dev, uint64_t n,
                        uint64_t out_affine[8], uint64_t *out_jacobian, uint8_t *out_compressed, void *stream);
+/* `batch` MSMs over the SAME bases in one pass (all advice columns of a phase are committed this way): scalar_cols_dev is a
+ * HOST array of `batch` device pointers (n scalars each); out_affine receives batch x 8 limbs.                              */
+ZKB_API int32_t zkb_msm_g1_batch_dev(zkb_ctx *ctx, const uint64_t *const *scalar_cols_dev, uint32_t batch,
+                                     const uint64_t *bases_dev, uint64_t n, uint64_t *out_affine, void *stream);
 /* Number of bucket additions + reduction additions the last MSM on this context performed (G1-adds metric). */
 ZKB_API uint64_t zkb_msm_last_adds(const zkb_ctx *ctx);
 

@@ -174,3 +174,26 @@ def test_msm_2_20_vs_oracle(A, oracle):
     exp = oracle.g1_to_affine(oracle.best_multiexp(to_host(s_t), to_host(bases_t)))
     assert r.compressed == oracle.g1_compress(exp)
     assert (r.affine == exp).all()
+
+
+def test_msm_batch_vs_single(A, oracle):
+    """Batched multi-column MSM (how a phase's advice columns are committed) == one MSM per column, incl. skewed columns."""
+    import torch
+    n = 1 << 13
+    bases = make_bases(A, oracle, n, 4242)
+    cols = [rand_field(n, 900 + i) for i in range(5)]
+    cols[1][:] = 0                                   # all-zero column -> identity commitment
+    cols[2][:, 1:] = 0; cols[2][:, 0] &= np.uint64(3)   # tiny Montgomery limbs pattern (structured column)
+    one = oracle.fr_from_canonical(np.array([[1, 0, 0, 0]], dtype=np.uint64))[0]
+    cols[3][:] = one                                 # every scalar equal: one giant bucket per window (skew path)
+    cols[3][::7] = 0
+    bt = to_dev(bases)
+    got = A.best_multiexp_batch_dev([to_dev(c) for c in cols], bt)
+    for c, g in zip(cols, got):
+        exp = oracle.g1_to_affine(oracle.best_multiexp(c, bases))
+        assert (g == exp).all()
+    # a batch larger than the internal per-pass limit
+    many = [to_dev(rand_field(n, 2000 + i)) for i in range(70)]
+    got = A.best_multiexp_batch_dev(many, bt)
+    for i in (0, 33, 69):
+        assert (got[i] == A.best_multiexp_dev(many[i], bt).affine).all()

@@ -122,6 +122,17 @@ def best_multiexp_dev(coeffs_t, bases_t, ctx=None):
     return MsmResult(aff, jac, bytes(comp))
 
 
+def best_multiexp_batch_dev(coeff_cols, bases_t, ctx=None):
+    """Commit several scalar columns (list of device tensors (n,4)) against the same bases in one batched pass.
+    Returns numpy uint64 (len(cols), 8) affine points."""
+    ctx = ctx or default_context(bases_t.device.index)
+    n = coeff_cols[0].shape[0]
+    ptrs = (ctypes.c_void_p * len(coeff_cols))(*[c.data_ptr() for c in coeff_cols])
+    out = np.zeros((len(coeff_cols), 8), dtype=np.uint64)
+    check(ctx.lib.zkb_msm_g1_batch_dev(ctx.handle, ctypes.cast(ptrs, _vp), len(coeff_cols), _vp(bases_t.data_ptr()), n, _np_ptr(out), _cur_stream()))
+    return out
+
+
 def msm_last_adds(ctx=None):
     ctx = ctx or default_context()
     return int(ctx.lib.zkb_msm_last_adds(ctx.handle))

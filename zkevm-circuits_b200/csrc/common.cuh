@@ -63,7 +63,7 @@ struct zkb_ctx {
     uint64_t msm_last_adds = 0;
     std::map<std::array<uint64_t, 5>, zkb::NttPlan> ntt_plans;
     // grow-only scratch arenas (device), keyed by purpose; avoids cudaMalloc in steady state
-    zkb::DeviceBuffer scratch[8];
+    zkb::DeviceBuffer scratch[12];
     void *pinned = nullptr;  // small pinned staging buffer
     size_t pinned_bytes = 0;
 };
@@ -81,6 +81,10 @@ int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src, Fr *dst, uint32_t log_n, cons
                       const Fr *d_in_scale, cudaStream_t st);
 // synchronises: the result point is returned to the host
 int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, uint64_t n, G1Affine *out_affine_host, cudaStream_t st);
+// `batch` MSMs over the same bases in one pass (d_scalar_cols: DEVICE array of device pointers; batch <= msm_max_batch(n))
+uint32_t msm_max_batch(uint64_t n);
+int32_t msm_g1_batch_device(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32_t batch, const G1Affine *bases, uint64_t n,
+                            G1Affine *out_affine_host, cudaStream_t st);
 int32_t fr_powers_device(zkb_ctx *ctx, const Fr &base, uint64_t n, Fr *out, cudaStream_t st);
 int32_t poly_eval_device(zkb_ctx *ctx, const Fr *const *d_polys, uint32_t num, uint64_t n, const Fr &x, Fr *out_host, cudaStream_t st);
 int32_t prefix_product_device(zkb_ctx *ctx, const Fr *in, uint64_t n, const Fr &init, Fr *out, cudaStream_t st);
@@ -89,5 +93,5 @@ int32_t kate_division_device(zkb_ctx *ctx, const Fr *a, uint64_t n, const Fr &u,
 int32_t lincomb_device(zkb_ctx *ctx, const Fr *const *d_polys, const Fr *d_coefs, uint32_t num, uint64_t n, Fr *out, bool accumulate, cudaStream_t st);
 int32_t batch_invert_device(zkb_ctx *ctx, const Fr *a, Fr *out, uint64_t n, cudaStream_t st);
 
-enum ScratchSlot { SCR_NTT = 0, SCR_MSM_A = 1, SCR_MSM_B = 2, SCR_MSM_C = 3, SCR_HOSTIO_A = 4, SCR_HOSTIO_B = 5, SCR_MISC = 6, SCR_MISC2 = 7 };
+enum ScratchSlot { SCR_NTT = 0, SCR_MSM_A = 1, SCR_MSM_B = 2, SCR_MSM_C = 3, SCR_HOSTIO_A = 4, SCR_HOSTIO_B = 5, SCR_MISC = 6, SCR_MISC2 = 7, SCR_MSM_TBL = 8 };
 }  // namespace zkb

@@ -51,11 +51,12 @@ __device__ __forceinline__ uint32_t raw_window(const uint32_t s[8], uint32_t bit
 
 // mode 0: histogram; mode 1: scatter
 template <int MODE>
-__global__ void msm_digits_kernel(const Fr *__restrict__ scalars, uint64_t n, MsmCfg m, uint32_t *__restrict__ counts,
+__global__ void msm_digits_kernel(const Fr *const *__restrict__ scalar_cols, uint64_t n, MsmCfg m, uint32_t *__restrict__ counts,
                                   uint32_t *__restrict__ cursors, uint32_t *__restrict__ sorted) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Fr s = fp_to_canonical(fp_load(scalars + i));
+    const uint32_t col_base = blockIdx.y * m.windows * m.half;  // one bucket set per column of the batch
+    const Fr s = fp_to_canonical(fp_load(scalar_cols[blockIdx.y] + i));
     uint32_t carry = 0;
     for (uint32_t w = 0; w < m.windows; ++w) {
         const uint32_t bit = w * m.c;
@@ -64,7 +65,7 @@ __global__ void msm_digits_kernel(const Fr *__restrict__ scalars, uint64_t n, Ms
         if (d > m.half) { d = (1u << m.c) - d; neg = 1; carry = 1; }
         else carry = 0;
         if (d != 0) {
-            const uint32_t b = w * m.half + (d - 1);
+            const uint32_t b = col_base + w * m.half + (d - 1);
             if (MODE == 0) atomicAdd(&counts[b], 1u);
             else {
                 const uint32_t pos = atomicAdd(&cursors[b], 1u);
@@ -291,17 +292,29 @@ __global__ void __launch_bounds__(128) fixed_base_mul_kernel(G1Affine base, cons
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, uint64_t n, G1Affine *out_affine_host, cudaStream_t st) {
-    ZKB_ARG(n < (1ull << 31));
+uint32_t msm_max_batch(uint64_t n) {
+    if (n == 0) return 64;
+    const MsmCfg m = choose_cfg(n);
+    uint64_t b = (1ull << 28) / (n * m.windows);
+    if (b < 1) b = 1;
+    if (b > 64) b = 64;
+    return (uint32_t)b;
+}
+
+// batch of `batch` MSMs over the same bases: d_scalar_cols is a DEVICE array of `batch` device pointers
+int32_t msm_g1_batch_device(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32_t batch, const G1Affine *bases, uint64_t n,
+                            G1Affine *out_affine_host, cudaStream_t st) {
+    ZKB_ARG(n < (1ull << 31) && batch >= 1);
     if (n == 0) {
-        memset(out_affine_host, 0, sizeof(G1Affine));
+        memset(out_affine_host, 0, sizeof(G1Affine) * batch);
         ctx->msm_last_adds = 0;
         return ZKB_OK;
     }
-    const MsmCfg m = choose_cfg(n);
-    const uint32_t nbuckets = m.windows * m.half;
-    const uint64_t pairs = n * m.windows;
-    ZKB_ARG(pairs < (1ull << 32));
+    MsmCfg m = choose_cfg(n);
+    const uint32_t windows1 = m.windows;          // windows per column
+    const uint32_t nbuckets = batch * windows1 * m.half;
+    const uint64_t pairs = n * windows1 * batch;
+    ZKB_ARG(pairs < (1ull << 32) && (uint64_t)batch * windows1 * m.half < (1ull << 31));
     const uint32_t log_l = 5;  // window-reduction segment length 32
 
     // scratch A: counts | offsets(+1) | cursors | tcount | toffA(+1) | toffB(+1) | scan tmp | max
@@ -317,11 +330,13 @@ int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, ui
 
     ZKB_CUDA(cudaMemsetAsync(counts, 0, cnt_bytes, st));
     ZKB_CUDA(cudaMemsetAsync(d_max, 0, 4, st));
-    const unsigned tb = 256, gb = (unsigned)((n + tb - 1) / tb), bb = (nbuckets + 255) / 256;
-    msm_digits_kernel<0><<<gb, tb, 0, st>>>(scalars, n, m, counts, nullptr, nullptr);
+    const unsigned tb = 256, bb = (nbuckets + 255) / 256;
+    const dim3 gb((unsigned)((n + tb - 1) / tb), batch);
+    msm_digits_kernel<0><<<gb, tb, 0, st>>>(d_scalar_cols, n, m, counts, nullptr, nullptr);
     exclusive_scan_u32(ctx, counts, offsets, nbuckets, scan_tmp, st);
     ZKB_CUDA(cudaMemcpyAsync(cursors, offsets, (size_t)nbuckets * 4, cudaMemcpyDeviceToDevice, st));
-    msm_digits_kernel<1><<<gb, tb, 0, st>>>(scalars, n, m, nullptr, cursors, sorted);
+    msm_digits_kernel<1><<<gb, tb, 0, st>>>(d_scalar_cols, n, m, nullptr, cursors, sorted);
+    m.windows = windows1 * batch;  // from here on a (column, window) pair is just a window
     max_u32_kernel<<<64, 256, 0, st>>>(offsets, nbuckets, d_max);
     task_count_kernel<<<bb, 256, 0, st>>>(offsets, nbuckets, tcount);
     exclusive_scan_u32(ctx, tcount, toff[0], nbuckets, scan_tmp, st);
@@ -402,15 +417,30 @@ int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, ui
     std::vector<G1Xyzz> h(m.windows);
     ZKB_CUDA(cudaMemcpyAsync(h.data(), wres, m.windows * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
     ZKB_CUDA(cudaStreamSynchronize(st));
-    // Horner over windows on the host (W * c doublings + W additions of single points)
-    G1Xyzz acc = h[m.windows - 1];
-    for (int w = (int)m.windows - 2; w >= 0; --w) {
-        for (uint32_t k = 0; k < m.c; ++k) acc = g1_dbl(acc);
-        g1_add(acc, h[w]);
+    // Horner over windows on the host (W * c doublings + W additions of single points), per column
+    for (uint32_t col = 0; col < batch; ++col) {
+        const G1Xyzz *hw = h.data() + (size_t)col * windows1;
+        G1Xyzz acc = hw[windows1 - 1];
+        for (int w = (int)windows1 - 2; w >= 0; --w) {
+            for (uint32_t k = 0; k < m.c; ++k) acc = g1_dbl(acc);
+            g1_add(acc, hw[w]);
+        }
+        out_affine_host[col] = g1_to_affine(acc);
     }
-    *out_affine_host = g1_to_affine(acc);
     ctx->msm_last_adds = (uint64_t)total_pairs + extra_adds + 2ull * nbuckets;
     return ZKB_OK;
+}
+
+int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, uint64_t n, G1Affine *out_affine_host, cudaStream_t st) {
+    if (n == 0) {
+        memset(out_affine_host, 0, sizeof(G1Affine));
+        ctx->msm_last_adds = 0;
+        return ZKB_OK;
+    }
+    const Fr **d_tbl = nullptr;
+    ZKB_TRY(scratch_get(ctx, SCR_MSM_TBL, 64 * sizeof(Fr *), (void **)&d_tbl));
+    ZKB_CUDA(cudaMemcpyAsync(d_tbl, &scalars, sizeof(Fr *), cudaMemcpyHostToDevice, st));
+    return msm_g1_batch_device(ctx, d_tbl, 1, bases, n, out_affine_host, st);
 }
 
 }  // namespace zkb
@@ -448,6 +478,22 @@ extern "C" int32_t zkb_msm_g1_host(zkb_ctx *ctx, const uint64_t *scalars_host, c
         ZKB_CUDA(cudaMemcpyAsync(db, bases_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     }
     return zkb_msm_g1_dev(ctx, (const uint64_t *)ds, (const uint64_t *)db, n, out_affine, out_jacobian, out_compressed, ctx->stream);
+}
+
+extern "C" int32_t zkb_msm_g1_batch_dev(zkb_ctx *ctx, const uint64_t *const *scalar_cols_dev, uint32_t batch, const uint64_t *bases_dev, uint64_t n,
+                                        uint64_t *out_affine, void *stream) {
+    ZKB_ARG(ctx && scalar_cols_dev && bases_dev && out_affine && batch >= 1);
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    const uint32_t maxb = msm_max_batch(n);
+    for (uint32_t done = 0; done < batch; done += maxb) {
+        const uint32_t cur = batch - done < maxb ? batch - done : maxb;
+        const Fr **d_tbl = nullptr;
+        ZKB_TRY(scratch_get(ctx, SCR_MSM_TBL, 64 * sizeof(Fr *), (void **)&d_tbl));
+        ZKB_CUDA(cudaMemcpyAsync(d_tbl, scalar_cols_dev + done, cur * sizeof(Fr *), cudaMemcpyHostToDevice, st));
+        ZKB_TRY(msm_g1_batch_device(ctx, d_tbl, cur, (const G1Affine *)bases_dev, n, (G1Affine *)out_affine + done, st));
+    }
+    return ZKB_OK;
 }
 
 extern "C" int32_t zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_affine_host[8], const uint64_t *scalars_dev, uint64_t n,

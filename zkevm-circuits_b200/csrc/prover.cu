@@ -250,6 +250,20 @@ static int32_t commit(zkb_pk *pk, const Fr *scalars, const G1Affine *bases, uint
     return msm_g1_device(pk->ctx, scalars, bases, len, out, st);
 }
 
+// commit several columns against the same bases with batched MSMs (one pass per <= msm_max_batch columns)
+static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Affine *bases, uint64_t len, std::vector<G1Affine> &out, cudaStream_t st) {
+    out.resize(cols.size());
+    const uint32_t maxb = msm_max_batch(len);
+    for (size_t done = 0; done < cols.size(); done += maxb) {
+        const uint32_t cur = (uint32_t)std::min<size_t>(maxb, cols.size() - done);
+        const Fr **d_tbl = nullptr;
+        ZKB_TRY(scratch_get(pk->ctx, SCR_MSM_TBL, 64 * sizeof(Fr *), (void **)&d_tbl));
+        ZKB_CUDA(cudaMemcpyAsync(d_tbl, cols.data() + done, cur * sizeof(Fr *), cudaMemcpyHostToDevice, st));
+        ZKB_TRY(msm_g1_batch_device(pk->ctx, d_tbl, cur, bases, len, out.data() + done, st));
+    }
+    return ZKB_OK;
+}
+
 // program bundle uploaded to the device
 struct DeviceProgram {
     Instr *code = nullptr;
@@ -437,15 +451,17 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
     ZKB_CUDA(cudaSetDevice(pk->ctx->device));
     cudaStream_t st = pk->ctx->stream;
     const uint64_t n = pk->n;
+    std::vector<Fr *> phase_cols;
     for (uint32_t c = 0; c < cs.na; ++c) {
         if (cs.adv_phase[c] != phase) continue;
         ZKB_ARG(advice_columns[c] != nullptr);
         ZKB_TRY(s->pool.fr(n, &s->adv_values[c]));
         ZKB_CUDA(cudaMemcpyAsync(s->adv_values[c], advice_columns[c], n * sizeof(Fr), cudaMemcpyHostToDevice, st));
-        G1Affine cm;
-        ZKB_TRY(commit(pk, s->adv_values[c], pk->g_lagrange, n, &cm, st));
-        ZKB_TRY(tr_write_point(s, cm));
+        phase_cols.push_back(s->adv_values[c]);
     }
+    std::vector<G1Affine> cms;
+    ZKB_TRY(commit_many(pk, phase_cols, pk->g_lagrange, n, cms, st));
+    for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
     for (uint32_t i = 0; i < cs.nch; ++i) {
         if (cs.ch_phase[i] == phase) {
             s->challenges[i] = tr_squeeze(s);
@@ -571,9 +587,11 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_CUDA(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
         ZKB_CUDA(cudaStreamSynchronize(st));
         if (herr) { set_error("lookup %zu: an input row is not in the table (unsatisfied witness)", l); return ZKB_ERR_ARG; }
-        G1Affine cm;
-        ZKB_TRY(commit(pk, lk_m[l], pk->g_lagrange, n, &cm, st));
-        ZKB_TRY(tr_write_point(s, cm));
+    }
+    {
+        std::vector<G1Affine> cms;
+        ZKB_TRY(commit_many(pk, lk_m, pk->g_lagrange, n, cms, st));
+        for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
     }
 
     trace.mark("lookups: compress + m + commit");
@@ -628,10 +646,10 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
             ZKB_CUDA(cudaStreamSynchronize(st));
         }
     }
-    for (uint32_t si = 0; si < pk->nsets; ++si) {
-        G1Affine cm;
-        ZKB_TRY(commit(pk, zs[si], pk->g_lagrange, n, &cm, st));
-        ZKB_TRY(tr_write_point(s, cm));
+    {
+        std::vector<G1Affine> cms;
+        ZKB_TRY(commit_many(pk, zs, pk->g_lagrange, n, cms, st));
+        for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
     }
 
     trace.mark("permutation z + commit");
@@ -685,10 +703,10 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(prefix_sum_device(ctx, dterm, n, Fr::zero(), phis[l], st));
         ZKB_CUDA(cudaMemcpyAsync(phis[l] + (n - bf), phi_blinds + 4ull * bf * l, (size_t)bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
     }
-    for (size_t l = 0; l < nl; ++l) {
-        G1Affine cm;
-        ZKB_TRY(commit(pk, phis[l], pk->g_lagrange, n, &cm, st));
-        ZKB_TRY(tr_write_point(s, cm));
+    {
+        std::vector<G1Affine> cms;
+        ZKB_TRY(commit_many(pk, phis, pk->g_lagrange, n, cms, st));
+        for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
     }
 
     trace.mark("lookup phi + commit");
@@ -844,10 +862,12 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     trace.mark("quotient: coset NTTs + fused eval");
     // extended_to_coeff: inverse NTT over the extended domain, 1/N, undo the zeta coset, keep n*(d-1) coefficients
     ZKB_TRY(ntt_fr_device(ctx, h_ext, h_ext, pk->ext_k, pk->ext_omega_inv, &pk->N_inv, 2, nullptr, st));
-    for (uint32_t i = 0; i < pk->qdeg; ++i) {
-        G1Affine cm;
-        ZKB_TRY(commit(pk, h_ext + (size_t)i * n, pk->g, n, &cm, st));
-        ZKB_TRY(tr_write_point(s, cm));
+    {
+        std::vector<Fr *> pcs;
+        for (uint32_t i = 0; i < pk->qdeg; ++i) pcs.push_back(h_ext + (size_t)i * n);
+        std::vector<G1Affine> cms;
+        ZKB_TRY(commit_many(pk, pcs, pk->g, n, cms, st));
+        for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
     }
     const Fr x = tr_squeeze(s);
     const Fr xn = fp_pow_u64(x, n);
