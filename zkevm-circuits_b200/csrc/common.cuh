@@ -79,6 +79,9 @@ Fr host_zeta();
 // dst <- NTT_omega(src * in_scale) * scale ; src == dst allowed; coset_zeta as in zkb_ntt_fr_dev
 int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src, Fr *dst, uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta,
                       const Fr *d_in_scale, cudaStream_t st);
+// `count` transforms in one launch per pass: column y reads d_src_tbl[y], writes d_dst_tbl[y] (device pointer tables)
+int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *src, Fr *dst, const Fr *const *d_src_tbl, Fr *const *d_dst_tbl, uint32_t count, uint32_t log_n,
+                            const Fr &omega, const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, cudaStream_t st);
 // synchronises: the result point is returned to the host
 int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, uint64_t n, G1Affine *out_affine_host, cudaStream_t st);
 // `batch` MSMs over the same bases in one pass (d_scalar_cols: DEVICE array of device pointers; batch <= msm_max_batch(n))

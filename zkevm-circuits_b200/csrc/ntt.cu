@@ -39,18 +39,66 @@ struct PassArgs {
     const Fr *tw_hi;
     const Fr *scale;
     const Fr *in_scale;  // optional per-element input multiplier (first pass only): coset scaling tables
+    // batching over blockIdx.y: column y reads in_tbl[y] (or in + y * in_stride) and writes out_tbl[y] (or out + y * out_stride)
+    const Fr *const *in_tbl;
+    Fr *const *out_tbl;
+    uint64_t in_stride, out_stride;
 };
 
+// element i lives at slot i ^ ((i >> 3) & 7): keeps unit-stride runs conflict free AND makes the stride-8 accesses of the
+// last radix-8 round (a thread owns 8 consecutive elements) hit 8 distinct 16-byte bank groups
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u); }
 __device__ __forceinline__ Fr smem_ld(const uint4 *lo, const uint4 *hi, uint32_t i) {
-    uint4 a = lo[i], b = hi[i];
+    const uint32_t k = swz(i);
+    uint4 a = lo[k], b = hi[k];
     Fr r;
     r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
 __device__ __forceinline__ void smem_st(uint4 *lo, uint4 *hi, uint32_t i, const Fr &v) {
-    lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-    hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    const uint32_t k = swz(i);
+    lo[k] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[k] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// R consecutive DIF stages (s .. s+R-1) on groups of 2^R elements held in registers: one shared-memory round trip and
+// one barrier per R stages; the 2^R - 1 distinct twiddles of a group are loaded once.
+template <int R>
+__device__ __forceinline__ void ntt_round(uint4 *lo, uint4 *hi, uint32_t a, uint32_t s, const Fr *__restrict__ loc, uint32_t tid, uint32_t nt) {
+    constexpr int E = 1 << R;
+    const uint32_t A = 1u << a;
+    const uint32_t h = A >> (s + 1);
+    const uint32_t q = h >> (R - 1);          // spacing of the group's elements = half distance of the round's last stage
+    const uint32_t lq = 31 - __clz(q);
+    for (uint32_t g = tid; g < (A >> R); g += nt) {
+        const uint32_t p_local = g & (q - 1);
+        const uint32_t base = ((g >> lq) << (lq + R)) + p_local;
+        Fr x[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) x[m] = smem_ld(lo, hi, base + ((uint32_t)m << lq));
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int d = E >> (t + 1);
+            const bool last_trivial = ((uint32_t)d << lq) == 1u;   // half distance 1: twiddle is omega^0
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                if ((m & d) == 0) {
+                    const Fr u = x[m], v = x[m + d];
+                    x[m] = fp_add(u, v);
+                    Fr dif = fp_sub(u, v);
+                    if (!last_trivial) {
+                        const uint32_t pos = p_local + ((uint32_t)(m & (d - 1)) << lq);
+                        dif = fp_mul(dif, fp_load(loc + ((size_t)pos << (s + t))));
+                    }
+                    x[m + d] = dif;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < E; ++m) smem_st(lo, hi, base + ((uint32_t)m << lq), x[m]);
+    }
 }
 __device__ __forceinline__ Fr zeta_pow(int i) {  // i in {1,2}
     Fr z;
@@ -59,8 +107,10 @@ __device__ __forceinline__ Fr zeta_pow(int i) {  // i in {1,2}
     return z;
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(const Fr *__restrict__ in, Fr *__restrict__ out, PassArgs p) {
+__global__ void __launch_bounds__(512) ntt_pass_kernel(const Fr *__restrict__ in_base, Fr *__restrict__ out_base, PassArgs p) {
     extern __shared__ uint4 smem[];
+    const Fr *__restrict__ in = p.in_tbl ? p.in_tbl[blockIdx.y] : in_base + (size_t)blockIdx.y * p.in_stride;
+    Fr *__restrict__ out = p.out_tbl ? p.out_tbl[blockIdx.y] : out_base + (size_t)blockIdx.y * p.out_stride;
     const uint32_t A = 1u << p.a;
     uint4 *lo = smem, *hi = smem + A;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -81,21 +131,12 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const Fr *__restrict__ in
     }
     __syncthreads();
 
-    // decimation in frequency: natural order in, bit-reversed order out (inside shared memory)
-    for (uint32_t s = 0; s < p.a; ++s) {
-        const uint32_t h = A >> (s + 1);
-        for (uint32_t t = tid; t < (A >> 1); t += nt) {
-            const uint32_t pos = t & (h - 1);
-            const uint32_t i = ((t >> (p.a - 1 - s)) << (p.a - s)) + pos;
-            const uint32_t j = i + h;
-            const Fr u = smem_ld(lo, hi, i), v = smem_ld(lo, hi, j);
-            const Fr sum = fp_add(u, v);
-            Fr dif = fp_sub(u, v);
-            if (h > 1) dif = fp_mul(dif, fp_load(p.loc + ((size_t)pos << s)));
-            smem_st(lo, hi, i, sum);
-            smem_st(lo, hi, j, dif);
-        }
-        __syncthreads();
+    // decimation in frequency: natural order in, bit-reversed order out (inside shared memory); radix-8 rounds in registers
+    {
+        uint32_t s = 0;
+        while (p.a - s >= 3) { ntt_round<3>(lo, hi, p.a, s, p.loc, tid, nt); __syncthreads(); s += 3; }
+        if (p.a - s == 2) { ntt_round<2>(lo, hi, p.a, s, p.loc, tid, nt); __syncthreads(); }
+        else if (p.a - s == 1) { ntt_round<1>(lo, hi, p.a, s, p.loc, tid, nt); __syncthreads(); }
     }
 
     for (uint32_t q = tid; q < A; q += nt) {
@@ -208,9 +249,11 @@ static int32_t get_plan(zkb_ctx *ctx, uint32_t log_n, const Fr &omega, NttPlan *
 
 static bool g_attr_set = false;
 
-int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta,
-                      const Fr *d_in_scale, cudaStream_t st) {
-    ZKB_ARG(log_n <= 3 * NTT_MAX_BITS && log_n <= 28);
+// batch of `count` transforms: column y reads d_src_tbl[y], writes d_dst_tbl[y] (device pointer tables; tables may alias).
+// With count == 1 and null tables, src/dst are used directly.
+int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, const Fr *const *d_src_tbl, Fr *const *d_dst_tbl, uint32_t count,
+                            uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, cudaStream_t st) {
+    ZKB_ARG(log_n <= 3 * NTT_MAX_BITS && log_n <= 28 && count >= 1);
     ZKB_ARG(coset_zeta >= 0 && coset_zeta <= 2);
     NttPlan *plan = nullptr;
     ZKB_TRY(get_plan(ctx, log_n, omega, &plan));
@@ -220,7 +263,7 @@ int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, uint32_t log_n
     }
     const uint64_t n = 1ull << log_n;
     Fr *scratch = nullptr;
-    if (plan->npass > 1) ZKB_TRY(scratch_get(ctx, SCR_NTT, n * sizeof(Fr), (void **)&scratch));
+    if (plan->npass > 1) ZKB_TRY(scratch_get(ctx, SCR_NTT, (size_t)count * n * sizeof(Fr), (void **)&scratch));
 
     // scale: folded into the two-level twiddle table for multi-pass transforms
     Fr *d_scale = nullptr;
@@ -250,7 +293,7 @@ int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, uint32_t log_n
         p.is_final = (ps == plan->npass - 1);
         uint32_t consumed = 0;
         for (int q = 0; q <= ps; ++q) consumed += plan->bits[q];
-        p.tw_shift = consumed - a;  // n / (A * inner * outer_count) ... = bits consumed by earlier passes
+        p.tw_shift = consumed - a;  // bits consumed by the earlier passes
         p.a1 = p.a2 = 0;
         if (p.is_final) {
             if (plan->npass == 2) { p.a1 = plan->bits[0]; }
@@ -260,27 +303,35 @@ int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, uint32_t log_n
         p.coset_out = (p.is_final && coset_zeta == 2);
         p.use_scale = (plan->npass == 1 && scale_host != nullptr);
         p.loc = plan->loc[ps];
-        // only the first boundary carries the folded scale
-        p.tw_lo = (ps == 0) ? tw_lo : plan->tw_lo;
+        p.tw_lo = (ps == 0) ? tw_lo : plan->tw_lo;  // only the first boundary carries the folded scale
         p.tw_hi = plan->tw_hi;
         p.scale = d_scale;
         p.in_scale = (ps == 0) ? d_in_scale : nullptr;
-        const Fr *src;
-        Fr *dst;
-        if (plan->npass == 1) { src = src_data; dst = data; }
-        else if (ps == 0) { src = src_data; dst = scratch; }
-        else if (p.is_final) { src = scratch; dst = data; }
-        else { src = scratch; dst = scratch; }
+        p.in_tbl = nullptr;
+        p.out_tbl = nullptr;
+        p.in_stride = p.out_stride = 0;
+        const Fr *src = nullptr;
+        Fr *dst = nullptr;
+        const bool first = (ps == 0), last = p.is_final;
+        if (first) { if (d_src_tbl) p.in_tbl = d_src_tbl; else src = src_data; }
+        else { src = scratch; p.in_stride = n; }
+        if (last) { if (d_dst_tbl) p.out_tbl = d_dst_tbl; else dst = data; }
+        else { dst = scratch; p.out_stride = n; }
         const uint32_t A = 1u << a;
-        uint32_t threads = A / 2;
-        if (threads < 32) threads = 32;
+        uint32_t threads = A / 8;  // one radix-8 group per thread and round
+        if (threads < 64) threads = 64;
         if (threads > 512) threads = 512;
         const uint64_t blocks = n >> a;
-        ntt_pass_kernel<<<(unsigned)blocks, threads, (size_t)A * 32, st>>>(src, dst, p);
+        ntt_pass_kernel<<<dim3((unsigned)blocks, count), threads, (size_t)A * 32, st>>>(src, dst, p);
         ctx->launches++;
     }
     ZKB_CUDA(cudaGetLastError());
     return ZKB_OK;
+}
+
+int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta,
+                      const Fr *d_in_scale, cudaStream_t st) {
+    return ntt_fr_batch_device(ctx, src_data, data, nullptr, nullptr, 1, log_n, omega, scale_host, coset_zeta, d_in_scale, st);
 }
 
 }  // namespace zkb

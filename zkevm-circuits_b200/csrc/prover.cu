@@ -723,13 +723,23 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
 
     trace.mark("random poly commit");
     // ---------------------------------------------------------------- coefficient forms
-    auto to_coeff_new = [&](const std::vector<Fr *> &vals, std::vector<Fr *> &polys) -> int32_t {
-        polys.resize(vals.size());
-        for (size_t i = 0; i < vals.size(); ++i) {
-            ZKB_TRY(pool.fr(n, &polys[i]));
-            ZKB_TRY(lagrange_to_coeff(pk, vals[i], polys[i], st));
+    const uint32_t ntt_chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, (1ull << 31) / (n * sizeof(Fr))));  // <= 2 GiB of NTT scratch
+    auto ntt_many = [&](const std::vector<Fr *> &src, const std::vector<Fr *> &dst, const Fr &w, const Fr *scale, const Fr *in_scale) -> int32_t {
+        for (size_t done = 0; done < src.size(); done += ntt_chunk) {
+            const uint32_t cur = (uint32_t)std::min<size_t>(ntt_chunk, src.size() - done);
+            std::vector<Fr *> a(src.begin() + done, src.begin() + done + cur), b(dst.begin() + done, dst.begin() + done + cur);
+            Fr **d_a = nullptr, **d_b = nullptr;
+            ZKB_TRY(upload_table(pool, a, &d_a, st));
+            ZKB_TRY(upload_table(pool, b, &d_b, st));
+            ZKB_TRY(ntt_fr_batch_device(ctx, nullptr, nullptr, d_a, d_b, cur, k, w, scale, 0, in_scale, st));
         }
         return ZKB_OK;
+    };
+    auto to_coeff_new = [&](const std::vector<Fr *> &vals, std::vector<Fr *> &polys) -> int32_t {
+        polys.resize(vals.size());
+        for (size_t i = 0; i < vals.size(); ++i) ZKB_TRY(pool.fr(n, &polys[i]));
+        if (vals.empty()) return ZKB_OK;
+        return ntt_many(vals, polys, pk->omega_inv, &pk->n_inv, nullptr);
     };
     std::vector<Fr *> adv_polys, z_polys, phi_polys, m_polys;
     ZKB_TRY(to_coeff_new(s->adv_values, adv_polys));
@@ -853,7 +863,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     for (uint32_t j = 0; j < pk->E; ++j) {
         const Fr gj = fp_mul(pk->zeta, fp_pow_u64(pk->ext_omega, j));
         ZKB_TRY(fr_powers_device(ctx, gj, n, pows, st));
-        for (size_t i = 0; i < qpolys.size(); ++i) ZKB_TRY(ntt_fr_device(ctx, qpolys[i], qcols[i], k, pk->omega, nullptr, 0, pows, st));
+        ZKB_TRY(ntt_many(qpolys, qcols, pk->omega, nullptr, pows));
         Instr tail{OP_STOREACC, 0, 0, 0, 0u | (tinv_idx[j] << 8)};
         ZKB_CUDA(cudaMemcpyAsync(qdp.code + base_len, &tail, sizeof(Instr), cudaMemcpyHostToDevice, st));
         ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, pk->E, j, st));
