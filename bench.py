@@ -35,7 +35,7 @@ def dist_env():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (recipe in B200_PROFILING.md)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
 
     def __init__(self, index):
         self.index = index
@@ -43,7 +43,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -61,9 +61,11 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
+            if len(f) < 9:
                 continue
             try:
+                if float(f[8]) < 50:       # keep only samples taken under load (GPU utilisation >= 50 %)
+                    continue
                 sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
@@ -120,11 +122,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=150)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-msm", action="store_true")
+    ap.add_argument("--no-proof", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -168,13 +171,13 @@ def main():
         A.best_fft_dev(data, w, LOG_N)
         A.best_fft_dev(data, wi, LOG_N, scale=ninv)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         step_dev()
     barrier()
     assert torch.equal(data, orig), "round trip does not restore the input"
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -251,6 +254,18 @@ def main():
         extras["msm_2^20"] = {"ms": msm_ms, "g1_adds": adds, "g1_adds_per_s": world * adds / (msm_ms * 1e-3),
                               "alg_bytes": n * 96, "achieved_gbs": n * 96 / (msm_ms * 1e-3) / 1e9,
                               "frac_of_hbm": n * 96 / (msm_ms * 1e-3) / 1e9 / peak, "commitment": r.compressed.hex()}
+
+    if not args.no_proof and rank == 0:
+        # BASELINE configs[2]/[3] stand-ins: Keccak-shaped k=17 and SuperCircuit-shaped k=20 synthetic circuits,
+        # full create_proof through the C-ABI session (H2D of every advice column inside the timed region).
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import proof_bench
+        try:
+            extras["proof_keccak_shape_k17"] = proof_bench.run(17, 64, 8, 16, reps=3)
+            extras["proof_super_shape_k20"] = proof_bench.run(20, 64, 8, 16, reps=2)
+        except Exception as e:  # keep the headline line even if the extra fails
+            extras["proof_error"] = repr(e)
+    barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -64,6 +64,10 @@ struct zkb_ctx {
     std::map<std::array<uint64_t, 5>, zkb::NttPlan> ntt_plans;
     // grow-only scratch arenas (device), keyed by purpose; avoids cudaMalloc in steady state
     zkb::DeviceBuffer scratch[12];
+    // cached device blocks (size -> pointers) recycled between proving sessions: cudaMalloc/cudaFree of tens of GB per proof
+    // costs seconds and is wildly variable; blocks go back to the driver only at zkb_destroy
+    std::multimap<size_t, void *> block_cache;
+    size_t block_cache_bytes = 0;
     void *pinned = nullptr;  // small pinned staging buffer
     size_t pinned_bytes = 0;
 };
@@ -71,6 +75,9 @@ struct zkb_ctx {
 namespace zkb {
 // returns a device scratch buffer of at least `bytes` (slot-indexed, grow-only)
 int32_t scratch_get(zkb_ctx *ctx, int slot, size_t bytes, void **out);
+// cached block allocator (see zkb_ctx::block_cache)
+int32_t block_alloc(zkb_ctx *ctx, size_t bytes, void **out, size_t *got);
+void block_free(zkb_ctx *ctx, void *p, size_t bytes);
 inline cudaStream_t pick_stream(zkb_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
 
 // ---- cross-translation-unit device-side services (all launch on `st`, none synchronises unless stated) ----------------

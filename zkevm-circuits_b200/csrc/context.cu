@@ -36,6 +36,39 @@ int32_t scratch_get(zkb_ctx *ctx, int slot, size_t bytes, void **out) {
     *out = b.ptr;
     return ZKB_OK;
 }
+int32_t block_alloc(zkb_ctx *ctx, size_t bytes, void **out, size_t *got) {
+    if (bytes < 256) bytes = 256;
+    bytes = (bytes + 255) & ~(size_t)255;
+    auto it = ctx->block_cache.lower_bound(bytes);
+    if (it != ctx->block_cache.end() && it->first <= bytes + (bytes >> 2) + 4096) {  // reuse a block at most 25 % larger
+        *out = it->second;
+        *got = it->first;
+        ctx->block_cache_bytes -= it->first;
+        ctx->block_cache.erase(it);
+        return ZKB_OK;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        // release the cache and retry once
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &kv : ctx->block_cache) cudaFree(kv.second);
+        ctx->block_cache.clear();
+        ctx->block_cache_bytes = 0;
+        e = cudaMalloc(out, bytes);
+    }
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return ZKB_ERR_ALLOC;
+    }
+    *got = bytes;
+    return ZKB_OK;
+}
+void block_free(zkb_ctx *ctx, void *p, size_t bytes) {
+    if (!p) return;
+    ctx->block_cache.emplace(bytes, p);
+    ctx->block_cache_bytes += bytes;
+}
+
 }  // namespace zkb
 
 using namespace zkb;
@@ -80,6 +113,7 @@ extern "C" int32_t zkb_destroy(zkb_ctx *ctx) {
     }
     for (auto &b : ctx->scratch)
         if (b.ptr) cudaFree(b.ptr);
+    for (auto &kv : ctx->block_cache) cudaFree(kv.second);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

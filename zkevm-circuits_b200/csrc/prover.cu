@@ -164,12 +164,18 @@ static bool fr_less(const Fr &a, const Fr &b) {  // halo2curves Ord: canonical i
 }
 static Fr fr_pow_i64(const Fr &base, const Fr &base_inv, int64_t e) { return e >= 0 ? fp_pow_u64(base, (uint64_t)e) : fp_pow_u64(base_inv, (uint64_t)(-e)); }
 
-struct DevPool {  // owns device allocations of a pk / session
-    std::vector<void *> ptrs;
-    ~DevPool() { for (void *p : ptrs) cudaFree(p); }
+struct DevPool {  // owns device allocations of a pk / session; blocks are recycled through the context's block cache
+    zkb_ctx *ctx = nullptr;
+    std::vector<std::pair<void *, size_t>> ptrs;
+    ~DevPool() {
+        if (!ctx) return;
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &p : ptrs) block_free(ctx, p.first, p.second);
+    }
     int32_t alloc(size_t bytes, void **out) {
-        ZKB_CUDA(cudaMalloc(out, bytes ? bytes : 32));
-        ptrs.push_back(*out);
+        size_t got = 0;
+        ZKB_TRY(block_alloc(ctx, bytes ? bytes : 32, out, &got));
+        ptrs.push_back({*out, got});
         return ZKB_OK;
     }
     int32_t fr(uint64_t n, Fr **out) { return alloc(n * sizeof(Fr), (void **)out); }
@@ -326,6 +332,7 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
     ZKB_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<zkb_pk> pk(new zkb_pk());
     pk->ctx = ctx;
+    pk->pool.ctx = ctx;
     if (!parse_csf(csf, csf_words, pk->cs)) return ZKB_ERR_ARG;
     const Csf &cs = pk->cs;
     ZKB_ARG((cs.nf == 0 || fixed_values) && (cs.perm.empty() || sigma_values));
@@ -415,6 +422,7 @@ extern "C" int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4]
     ZKB_CUDA(cudaSetDevice(pk->ctx->device));
     std::unique_ptr<zkb_session> s(new zkb_session());
     s->pk = pk;
+    s->pool.ctx = pk->ctx;
     const Csf &cs = pk->cs;
     const uint64_t n = pk->n;
     cudaStream_t st = pk->ctx->stream;
