@@ -122,6 +122,14 @@ ZKB_API int32_t zkb_fr_prefix_sum_dev(zkb_ctx *ctx, const uint64_t *in_dev, uint
 ZKB_API int32_t zkb_kate_division_dev(zkb_ctx *ctx, const uint64_t *a_dev, uint64_t n, const uint64_t u[4],
                                       uint64_t *q_dev, void *stream);
 
+/* ---- multi-GPU building blocks (one process per GPU; collectives are issued by the host layer over NCCL) -----------------
+ * zkb_ntt_cross_dev       size-p transform across ranks after the all-to-all of a domain-sharded NTT:
+ *                         out[k][t] = sum_j in[j][t] * omega_p^(j k), in/out are p x len row-major, p in {1,2,4,8,16}
+ * zkb_g1_sum_affine_host  sum of per-rank MSM partial results (host buffers, 64 B each); host-only, needs no device   */
+ZKB_API int32_t zkb_ntt_cross_dev(zkb_ctx *ctx, const uint64_t *in_dev, uint64_t *out_dev, uint32_t p, uint64_t len,
+                                  const uint64_t omega_p[4], void *stream);
+ZKB_API int32_t zkb_g1_sum_affine_host(const uint64_t *points, uint64_t count, uint64_t out_affine[8], uint8_t *out_compressed);
+
 /* ---- create_proof: device-resident proving session --------------------------------------------------------------
  * Replaces the body of halo2_proofs::plonk::create_proof::<KZGCommitmentScheme<Bn256>, ProverSHPLONK, Challenge255, R,
  * Blake2bWrite, C> (plonk/prover.rs; called at circuit-benchmarks/src/super_circuit.rs:117-132 and, through
