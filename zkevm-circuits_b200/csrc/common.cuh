@@ -93,6 +93,11 @@ int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *src, Fr *dst, const Fr *cons
 int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, uint64_t n, G1Affine *out_affine_host, cudaStream_t st);
 // `batch` MSMs over the same bases in one pass (d_scalar_cols: DEVICE array of device pointers; batch <= msm_max_batch(n))
 uint32_t msm_max_batch(uint64_t n);
+// window-shifted precomputed bases (copy w = 2^(c w) P_i): one bucket set per column, no Horner
+uint32_t msm_shift_copies(uint64_t n);
+int32_t msm_build_shifted_bases(zkb_ctx *ctx, const G1Affine *bases, uint64_t n, G1Affine *out, cudaStream_t st);
+int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32_t batch, const G1Affine *bases, uint64_t n,
+                               G1Affine *out_affine_host, bool shifted, cudaStream_t st);
 int32_t msm_g1_batch_device(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32_t batch, const G1Affine *bases, uint64_t n,
                             G1Affine *out_affine_host, cudaStream_t st);
 int32_t fr_powers_device(zkb_ctx *ctx, const Fr &base, uint64_t n, Fr *out, cudaStream_t st);

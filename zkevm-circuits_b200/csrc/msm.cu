@@ -24,7 +24,9 @@ struct MsmCfg {
     uint32_t c;         // window bits
     uint32_t windows;   // W
     uint32_t half;      // 2^(c-1) buckets per window
-    uint32_t seg_log;   // log2 of buckets per reduction segment
+    uint32_t seg_log;   // unused
+    uint32_t shifted;   // 1: bases array holds W copies, copy w = 2^(c w) * P_i -> ONE bucket set per column, no Horner
+    uint32_t n32;       // points per copy (shifted mode)
 };
 
 static MsmCfg choose_cfg(uint64_t n) {
@@ -38,6 +40,8 @@ static MsmCfg choose_cfg(uint64_t n) {
     m.windows = (255 + m.c - 1) / m.c;
     m.half = 1u << (m.c - 1);
     m.seg_log = 0;
+    m.shifted = 0;
+    m.n32 = 0;
     return m;
 }
 
@@ -55,7 +59,7 @@ __global__ void msm_digits_kernel(const Fr *const *__restrict__ scalar_cols, uin
                                   uint32_t *__restrict__ cursors, uint32_t *__restrict__ sorted) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t col_base = blockIdx.y * m.windows * m.half;  // one bucket set per column of the batch
+    const uint32_t col_base = blockIdx.y * (m.shifted ? m.half : m.windows * m.half);  // one bucket set per column of the batch
     const Fr s = fp_to_canonical(fp_load(scalar_cols[blockIdx.y] + i));
     uint32_t carry = 0;
     for (uint32_t w = 0; w < m.windows; ++w) {
@@ -65,11 +69,11 @@ __global__ void msm_digits_kernel(const Fr *const *__restrict__ scalar_cols, uin
         if (d > m.half) { d = (1u << m.c) - d; neg = 1; carry = 1; }
         else carry = 0;
         if (d != 0) {
-            const uint32_t b = col_base + w * m.half + (d - 1);
+            const uint32_t b = col_base + (m.shifted ? 0u : w * m.half) + (d - 1);
             if (MODE == 0) atomicAdd(&counts[b], 1u);
             else {
                 const uint32_t pos = atomicAdd(&cursors[b], 1u);
-                sorted[pos] = (uint32_t)i | (neg << 31);
+                sorted[pos] = ((uint32_t)i + (m.shifted ? w * m.n32 : 0u)) | (neg << 31);
             }
         }
     }
@@ -277,6 +281,15 @@ __global__ void msm_window_combine_kernel(const G1Xyzz *__restrict__ level_sums,
     g1_store_xyzz(out + w, r);
 }
 
+// ---- window-shifted bases: out[i] = 2^c * in[i] (affine in, affine out) --------------------------------------------------
+__global__ void __launch_bounds__(128) msm_shift_bases_kernel(const G1Affine *__restrict__ in, G1Affine *__restrict__ out, uint64_t n, uint32_t c) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Xyzz p = G1Xyzz::from_affine(g1_load_affine(in + i));
+    for (uint32_t k = 0; k < c; ++k) p = g1_dbl(p);
+    g1_store_affine(out + i, g1_to_affine(p));
+}
+
 // ---- fixed-base scalar multiplication: out[i] = [s_i] base (affine) ------------------------------------------
 __global__ void __launch_bounds__(128) fixed_base_mul_kernel(G1Affine base, const Fr *__restrict__ scalars, uint64_t n, G1Affine *__restrict__ out) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -292,18 +305,57 @@ __global__ void __launch_bounds__(128) fixed_base_mul_kernel(G1Affine base, cons
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+uint32_t msm_shift_window_bits(uint64_t n);
 uint32_t msm_max_batch(uint64_t n) {
     if (n == 0) return 64;
     const MsmCfg m = choose_cfg(n);
     uint64_t b = (1ull << 28) / (n * m.windows);
+    const uint32_t cs = msm_shift_window_bits(n);
+    if (cs) {  // shifted mode: half * batch buckets of 128 B (+ partials): keep the bucket arrays under ~2 GiB
+        const uint64_t bb = (1ull << 31) / ((1ull << (cs - 1)) * 3 * sizeof(G1Xyzz));
+        if (bb < b) b = bb;
+    }
     if (b < 1) b = 1;
     if (b > 64) b = 64;
     return (uint32_t)b;
 }
 
 // batch of `batch` MSMs over the same bases: d_scalar_cols is a DEVICE array of `batch` device pointers
+// window bits used with precomputed shifted bases for n points (0 = not supported at this size)
+uint32_t msm_shift_window_bits(uint64_t n) {
+    uint32_t lg = 0;
+    while ((1ull << (lg + 1)) <= n) ++lg;
+    if (lg < 10 || lg > 22) return 0;
+    return lg > 20 ? 20 : lg;
+}
+uint32_t msm_shift_copies(uint64_t n) {
+    const uint32_t c = msm_shift_window_bits(n);
+    return c ? (255 + c - 1) / c : 0;
+}
+// out: copies x n affine points, copy w = 2^(c w) * bases
+int32_t msm_build_shifted_bases(zkb_ctx *ctx, const G1Affine *bases, uint64_t n, G1Affine *out, cudaStream_t st) {
+    const uint32_t c = msm_shift_window_bits(n), copies = msm_shift_copies(n);
+    ZKB_ARG(c != 0);
+    ZKB_CUDA(cudaMemcpyAsync(out, bases, n * sizeof(G1Affine), cudaMemcpyDeviceToDevice, st));
+    for (uint32_t w = 1; w < copies; ++w) {
+        msm_shift_bases_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(out + (size_t)(w - 1) * n, out + (size_t)w * n, n, c);
+        ctx->launches++;
+    }
+    ZKB_CUDA(cudaGetLastError());
+    return ZKB_OK;
+}
+
+int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32_t batch, const G1Affine *bases, uint64_t n,
+                               G1Affine *out_affine_host, bool shifted, cudaStream_t st);
+
 int32_t msm_g1_batch_device(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32_t batch, const G1Affine *bases, uint64_t n,
                             G1Affine *out_affine_host, cudaStream_t st) {
+    return msm_g1_batch_device_ex(ctx, d_scalar_cols, batch, bases, n, out_affine_host, false, st);
+}
+
+// shifted == true: `bases` holds msm_shift_copies(n) x n points built by msm_build_shifted_bases
+int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32_t batch, const G1Affine *bases, uint64_t n,
+                               G1Affine *out_affine_host, bool shifted, cudaStream_t st) {
     ZKB_ARG(n < (1ull << 31) && batch >= 1);
     if (n == 0) {
         memset(out_affine_host, 0, sizeof(G1Affine) * batch);
@@ -311,10 +363,20 @@ int32_t msm_g1_batch_device(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32
         return ZKB_OK;
     }
     MsmCfg m = choose_cfg(n);
-    const uint32_t windows1 = m.windows;          // windows per column
-    const uint32_t nbuckets = batch * windows1 * m.half;
+    if (shifted) {
+        m.c = msm_shift_window_bits(n);
+        ZKB_ARG(m.c != 0);
+        m.windows = (255 + m.c - 1) / m.c;
+        m.half = 1u << (m.c - 1);
+        m.shifted = 1;
+        m.n32 = (uint32_t)n;
+        ZKB_ARG((uint64_t)m.windows * n < (1ull << 31));
+    }
+    const uint32_t windows1 = m.windows;          // digit windows per column
+    const uint32_t rwin1 = shifted ? 1 : windows1;  // bucket sets (reduction windows) per column
+    const uint32_t nbuckets = batch * rwin1 * m.half;
     const uint64_t pairs = n * windows1 * batch;
-    ZKB_ARG(pairs < (1ull << 32) && (uint64_t)batch * windows1 * m.half < (1ull << 31));
+    ZKB_ARG(pairs < (1ull << 32) && (uint64_t)batch * rwin1 * m.half < (1ull << 31));
     const uint32_t log_l = 5;  // window-reduction segment length 32
 
     // scratch A: counts | offsets(+1) | cursors | tcount | toffA(+1) | toffB(+1) | scan tmp | max
@@ -336,7 +398,7 @@ int32_t msm_g1_batch_device(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32
     exclusive_scan_u32(ctx, counts, offsets, nbuckets, scan_tmp, st);
     ZKB_CUDA(cudaMemcpyAsync(cursors, offsets, (size_t)nbuckets * 4, cudaMemcpyDeviceToDevice, st));
     msm_digits_kernel<1><<<gb, tb, 0, st>>>(d_scalar_cols, n, m, nullptr, cursors, sorted);
-    m.windows = windows1 * batch;  // from here on a (column, window) pair is just a window
+    m.windows = rwin1 * batch;  // from here on a (column, bucket set) pair is just a window
     max_u32_kernel<<<64, 256, 0, st>>>(offsets, nbuckets, d_max);
     task_count_kernel<<<bb, 256, 0, st>>>(offsets, nbuckets, tcount);
     exclusive_scan_u32(ctx, tcount, toff[0], nbuckets, scan_tmp, st);
@@ -419,9 +481,9 @@ int32_t msm_g1_batch_device(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32
     ZKB_CUDA(cudaStreamSynchronize(st));
     // Horner over windows on the host (W * c doublings + W additions of single points), per column
     for (uint32_t col = 0; col < batch; ++col) {
-        const G1Xyzz *hw = h.data() + (size_t)col * windows1;
-        G1Xyzz acc = hw[windows1 - 1];
-        for (int w = (int)windows1 - 2; w >= 0; --w) {
+        const G1Xyzz *hw = h.data() + (size_t)col * rwin1;
+        G1Xyzz acc = hw[rwin1 - 1];
+        for (int w = (int)rwin1 - 2; w >= 0; --w) {
             for (uint32_t k = 0; k < m.c; ++k) acc = g1_dbl(acc);
             g1_add(acc, hw[w]);
         }

@@ -195,6 +195,11 @@ struct zkb_pk {
     std::vector<Fr *> fixed_values, fixed_polys, sigma_values, sigma_polys;
     Fr *l0_poly = nullptr, *llast_poly = nullptr, *lblind_poly = nullptr, *xid_poly = nullptr, *omega_pows = nullptr;
     G1Affine *g = nullptr, *g_lagrange = nullptr;
+    // coset evaluations of the proof-independent polynomials (fixed, sigma, l_0, l_last, l_blind, X) for every coset part,
+    // like upstream's pk.fixed_cosets / permutation cosets / l0 / l_last / l_active_row: [part][poly] -> n elements
+    std::vector<std::vector<Fr *>> coset_cache;
+    // window-shifted copies of the SRS (copy w = 2^(c w) * P_i) for the Pippenger variant with one bucket set per column
+    G1Affine *g_shift = nullptr, *g_lagrange_shift = nullptr;
 };
 
 struct zkb_session {
@@ -260,12 +265,14 @@ static int32_t commit(zkb_pk *pk, const Fr *scalars, const G1Affine *bases, uint
 static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Affine *bases, uint64_t len, std::vector<G1Affine> &out, cudaStream_t st) {
     out.resize(cols.size());
     const uint32_t maxb = msm_max_batch(len);
+    const G1Affine *shift = (bases == pk->g) ? pk->g_shift : (bases == pk->g_lagrange) ? pk->g_lagrange_shift : nullptr;
+    if (len != pk->n) shift = nullptr;
     for (size_t done = 0; done < cols.size(); done += maxb) {
         const uint32_t cur = (uint32_t)std::min<size_t>(maxb, cols.size() - done);
         const Fr **d_tbl = nullptr;
         ZKB_TRY(scratch_get(pk->ctx, SCR_MSM_TBL, 64 * sizeof(Fr *), (void **)&d_tbl));
         ZKB_CUDA(cudaMemcpyAsync(d_tbl, cols.data() + done, cur * sizeof(Fr *), cudaMemcpyHostToDevice, st));
-        ZKB_TRY(msm_g1_batch_device(pk->ctx, d_tbl, cur, bases, len, out.data() + done, st));
+        ZKB_TRY(msm_g1_batch_device_ex(pk->ctx, d_tbl, cur, shift ? shift : bases, len, out.data() + done, shift != nullptr, st));
     }
     return ZKB_OK;
 }
@@ -367,6 +374,18 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
     ZKB_TRY(pk->pool.alloc(n * sizeof(G1Affine), (void **)&pk->g_lagrange));
     ZKB_CUDA(cudaMemcpyAsync(pk->g, g, n * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
     ZKB_CUDA(cudaMemcpyAsync(pk->g_lagrange, g_lagrange, n * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
+    {
+        // window-shifted SRS copies unless they would exceed ZKB_MSM_SHIFT_GB (default 24) in total
+        const uint32_t copies = msm_shift_copies(n);
+        const char *env = getenv("ZKB_MSM_SHIFT_GB");
+        const double budget = (env ? atof(env) : 24.0) * 1e9;
+        if (copies && 2.0 * copies * n * sizeof(G1Affine) <= budget) {
+            ZKB_TRY(pk->pool.alloc((size_t)copies * n * sizeof(G1Affine), (void **)&pk->g_shift));
+            ZKB_TRY(pk->pool.alloc((size_t)copies * n * sizeof(G1Affine), (void **)&pk->g_lagrange_shift));
+            ZKB_TRY(msm_build_shifted_bases(ctx, pk->g, n, pk->g_shift, st));
+            ZKB_TRY(msm_build_shifted_bases(ctx, pk->g_lagrange, n, pk->g_lagrange_shift, st));
+        }
+    }
     // fixed / sigma columns: values and coefficient form
     auto ingest = [&](const uint64_t *const *src, size_t cnt, std::vector<Fr *> &vals, std::vector<Fr *> &polys) -> int32_t {
         vals.resize(cnt);
@@ -401,6 +420,29 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
     ZKB_TRY(lagrange_to_coeff(pk.get(), pk->llast_poly, pk->llast_poly, st));
     ZKB_TRY(lagrange_to_coeff(pk.get(), pk->lblind_poly, pk->lblind_poly, st));
     ZKB_TRY(fr_powers_device(ctx, pk->omega, n, pk->omega_pows, st));
+    {
+        // cache the coset evaluations of the static polynomials unless that would take more than ZKB_COSET_CACHE_GB (default 48)
+        std::vector<Fr *> stat;
+        for (auto q : pk->fixed_polys) stat.push_back(q);
+        for (auto q : pk->sigma_polys) stat.push_back(q);
+        stat.push_back(pk->l0_poly); stat.push_back(pk->llast_poly); stat.push_back(pk->lblind_poly); stat.push_back(pk->xid_poly);
+        const char *env = getenv("ZKB_COSET_CACHE_GB");
+        const double budget = (env ? atof(env) : 48.0) * 1e9;
+        if ((double)stat.size() * pk->N * sizeof(Fr) <= budget) {
+            Fr *pows = nullptr;
+            ZKB_TRY(pk->pool.fr(n, &pows));
+            pk->coset_cache.resize(pk->E);
+            for (uint32_t j = 0; j < pk->E; ++j) {
+                const Fr gj = fp_mul(pk->zeta, fp_pow_u64(pk->ext_omega, j));
+                ZKB_TRY(fr_powers_device(ctx, gj, n, pows, st));
+                pk->coset_cache[j].resize(stat.size());
+                for (size_t i = 0; i < stat.size(); ++i) {
+                    ZKB_TRY(pk->pool.fr(n, &pk->coset_cache[j][i]));
+                    ZKB_TRY(ntt_fr_device(ctx, stat[i], pk->coset_cache[j][i], cs.k, pk->omega, nullptr, 0, pows, st));
+                }
+            }
+        }
+    }
     ZKB_CUDA(cudaStreamSynchronize(st));
     *out = pk.release();
     return ZKB_OK;
@@ -724,7 +766,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     ZKB_CUDA(cudaMemcpyAsync(random_poly, random_poly_host, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
     {
         G1Affine cm;
-        ZKB_TRY(commit(pk, random_poly, pk->g, n, &cm, st));
+        { std::vector<Fr *> one_col{random_poly}; std::vector<G1Affine> r1; ZKB_TRY(commit_many(pk, one_col, pk->g, n, r1, st)); cm = r1[0]; }
         ZKB_TRY(tr_write_point(s, cm));
     }
     const Fr y = tr_squeeze(s);
@@ -864,20 +906,37 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     ZKB_TRY(pool.fr(pk->N, &h_ext));
     std::vector<Fr *> qcols(qpolys.size());
     for (size_t i = 0; i < qpolys.size(); ++i) qcols[i] = slab + i * n;
+    // slots served from the pk's coset cache: fixed [0, nf), sigma, l0 / l_last / l_blind / X
+    const bool cached = !pk->coset_cache.empty();
+    std::vector<int> cache_idx(qpolys.size(), -1);
+    if (cached) {
+        int ci = 0;
+        for (uint32_t i = 0; i < cs.nf; ++i) cache_idx[qsm.fixed0 + i] = ci++;
+        for (size_t i = 0; i < cs.perm.size(); ++i) cache_idx[q_sigma0 + i] = ci++;
+        cache_idx[q_l0] = ci++; cache_idx[q_llast] = ci++; cache_idx[q_lblind] = ci++; cache_idx[q_x] = ci++;
+    }
+    std::vector<Fr *> ntt_src, ntt_dst;
+    for (size_t i = 0; i < qpolys.size(); ++i) {
+        if (cache_idx[i] < 0) { ntt_src.push_back(qpolys[i]); ntt_dst.push_back(qcols[i]); }
+    }
     Fr **d_qcols = nullptr, **d_hout = nullptr;
-    ZKB_TRY(upload_table(pool, qcols, &d_qcols, st));
+    ZKB_TRY(pool.alloc(qcols.size() * sizeof(Fr *) + 8, (void **)&d_qcols));
     std::vector<Fr *> hout{h_ext};
     ZKB_TRY(upload_table(pool, hout, &d_hout, st));
     for (uint32_t j = 0; j < pk->E; ++j) {
         const Fr gj = fp_mul(pk->zeta, fp_pow_u64(pk->ext_omega, j));
         ZKB_TRY(fr_powers_device(ctx, gj, n, pows, st));
-        ZKB_TRY(ntt_many(qpolys, qcols, pk->omega, nullptr, pows));
+        ZKB_TRY(ntt_many(ntt_src, ntt_dst, pk->omega, nullptr, pows));
+        std::vector<Fr *> cols_j = qcols;
+        if (cached)
+            for (size_t i = 0; i < qpolys.size(); ++i)
+                if (cache_idx[i] >= 0) cols_j[i] = pk->coset_cache[j][cache_idx[i]];
         Instr tail{OP_STOREACC, 0, 0, 0, 0u | (tinv_idx[j] << 8)};
+        ZKB_CUDA(cudaMemcpyAsync(d_qcols, cols_j.data(), cols_j.size() * sizeof(Fr *), cudaMemcpyHostToDevice, st));
         ZKB_CUDA(cudaMemcpyAsync(qdp.code + base_len, &tail, sizeof(Instr), cudaMemcpyHostToDevice, st));
         ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, pk->E, j, st));
-        ZKB_CUDA(cudaStreamSynchronize(st));  // `tail` lives on the stack
+        ZKB_CUDA(cudaStreamSynchronize(st));  // `tail` and `cols_j` live on the stack
     }
-    trace.mark("quotient: coset NTTs + fused eval");
     // extended_to_coeff: inverse NTT over the extended domain, 1/N, undo the zeta coset, keep n*(d-1) coefficients
     ZKB_TRY(ntt_fr_device(ctx, h_ext, h_ext, pk->ext_k, pk->ext_omega_inv, &pk->N_inv, 2, nullptr, st));
     {
@@ -1079,7 +1138,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     }
     {
         G1Affine cm;
-        ZKB_TRY(commit(pk, hx, pk->g, n, &cm, st));
+        { std::vector<Fr *> one_col{hx}; std::vector<G1Affine> r1; ZKB_TRY(commit_many(pk, one_col, pk->g, n, r1, st)); cm = r1[0]; }
         ZKB_TRY(tr_write_point(s, cm));
     }
     const Fr su = tr_squeeze(s);
@@ -1127,7 +1186,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_CUDA(cudaStreamSynchronize(st));
         ZKB_TRY(kate_division_device(ctx, work, n, su, work2, st));
         G1Affine cm;
-        ZKB_TRY(commit(pk, work2, pk->g, n, &cm, st));
+        { std::vector<Fr *> one_col{work2}; std::vector<G1Affine> r1; ZKB_TRY(commit_many(pk, one_col, pk->g, n, r1, st)); cm = r1[0]; }
         ZKB_TRY(tr_write_point(s, cm));
     }
     trace.mark("shplonk");
