@@ -937,6 +937,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, pk->E, j, st));
         ZKB_CUDA(cudaStreamSynchronize(st));  // `tail` and `cols_j` live on the stack
     }
+    trace.mark("quotient: coset NTTs + fused eval");
     // extended_to_coeff: inverse NTT over the extended domain, 1/N, undo the zeta coset, keep n*(d-1) coefficients
     ZKB_TRY(ntt_fr_device(ctx, h_ext, h_ext, pk->ext_k, pk->ext_omega_inv, &pk->N_inv, 2, nullptr, st));
     {
