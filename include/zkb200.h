@@ -159,6 +159,11 @@ typedef struct zkb_session zkb_session;
 ZKB_API int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
                               const uint64_t *const *sigma_values, const uint64_t *g, const uint64_t *g_lagrange, zkb_pk **out);
 ZKB_API int32_t zkb_pk_destroy(zkb_pk *pk);
+/* VerifyingKey bytes in SerdeFormat::Processed layout (u32 BE k || u32 BE num_fixed || fixed || permutation commitments,
+ * compressed points; the layout of the reference fixture's vk).  out may be NULL to query the length.                     */
+ZKB_API int32_t zkb_pk_vk_bytes(zkb_pk *pk, uint8_t *out, uint64_t cap, uint64_t *len);
+/* Host-only structural validation of a CSF blob (no CUDA device needed); zkb_pk_create runs it first.                       */
+ZKB_API int32_t zkb_csf_validate(const uint32_t *csf, uint64_t csf_words);
 ZKB_API int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4], const uint64_t *const *instance_values,
                                 const uint32_t *instance_lens, zkb_session **out);
 ZKB_API int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const uint64_t *const *advice_columns,

@@ -41,3 +41,35 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(zkb200.ZkbError):
         zkb200.Context(0)
+
+
+def _toy_cs():
+    from zkb200 import plonk as Z
+    E = Z.Expression
+    cs = Z.ConstraintSystem(5, 2, 2, 1, [0, 0], [], 5, 4)
+    one = (0xac96341c4ffffffb, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f)
+    cs.gates = [E.Fixed(0) * (E.Advice(0) * E.Advice(1, 1) + (-E.Instance(0))), (E.Advice(0) + E.Constant(one)).scaled(one)]
+    cs.lookups = [([[E.Fixed(0) * E.Advice(1)]], [E.Fixed(1)])]
+    cs.perm_columns = [(Z.ADVICE, 0), (Z.INSTANCE, 0)]
+    cs.advice_queries, cs.fixed_queries, cs.instance_queries = [(0, 0), (1, 1), (1, 0)], [(0, 0), (1, 0)], [(0, 0)]
+    return cs
+
+
+def test_csf_roundtrip_and_validation():
+    """The CSF blob (constraint system across the C ABI) is validated host-side: well-formed accepted, corrupt rejected."""
+    import numpy as np
+    import zkb200
+    from zkb200 import plonk as Z
+    blob = _toy_cs().to_csf()
+    Z.validate_csf(blob)
+    assert blob[0] == Z.CSF_MAGIC and blob[1] == 5 and blob[11] == 2 and blob[12] == 1 and blob[13] == 2
+    for mutate in (lambda b: b.__setitem__(0, 0x12345678),          # bad magic
+                   lambda b: b.__setitem__(3, 1),                    # fewer advice columns than the nodes reference
+                   lambda b: b.__setitem__(9, int(b[9]) + 50),       # node count beyond the blob
+                   lambda b: b.__setitem__(7, 2)):                   # degree below the permutation argument's
+        bad = blob.copy()
+        mutate(bad)
+        with pytest.raises(zkb200.ZkbError):
+            Z.validate_csf(bad)
+    with pytest.raises(zkb200.ZkbError):
+        Z.validate_csf(blob[:20])

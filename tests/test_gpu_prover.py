@@ -84,3 +84,21 @@ def test_unsatisfied_lookup_is_reported():
     zb = np.concatenate([F.arr(b) for b in tc.blinds_ints["z"]]); pb = np.concatenate([F.arr(b) for b in tc.blinds_ints["phi"]])
     with pytest.raises(ZkbError):
         Z.create_proof(pk, F.arr([tc.transcript_repr])[0], [F.arr(c) for c in tc.instances], synth, zb, pb, F.arr(tc.blinds_ints["random_poly"]))
+
+
+def test_vk_bytes_processed_format():
+    """keygen commitments on the GPU in the reference's SerdeFormat::Processed vk layout (fixture: u32 BE k, u32 BE #fixed, points)."""
+    import pyref as P
+    from zkb200 import plonk as Z
+    tc = ToyCircuit(6, seed=3)
+    ref = H.Ref(tc.cs, 1234)
+    F = ref.F
+    fixed = [F.arr(c) for c in tc.fixed_ints]
+    pkr = ref.keygen(fixed, tc.copies)
+    pk = Z.ProvingKey(to_product_cs(tc.cs, ref.bf, ref.d), fixed, pkr["sigma_values"], ref.g, ref.g_lagrange)
+    vk = pk.vk_bytes()
+    assert int.from_bytes(vk[:4], "big") == 6 and int.from_bytes(vk[4:8], "big") == len(fixed)
+    pts = pkr["fixed_commitments"] + pkr["sigma_commitments"]
+    assert len(vk) == 8 + 32 * len(pts)
+    for i, aff in enumerate(pts):
+        assert vk[8 + 32 * i: 40 + 32 * i] == ref.o.g1_compress(aff)

@@ -58,6 +58,7 @@ struct DeviceBuffer {
 struct zkb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of witness columns overlaps the MSMs of the previous batch
     int sm_count = 148;
     uint64_t launches = 0;
     uint64_t msm_last_adds = 0;

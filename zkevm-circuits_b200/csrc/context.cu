@@ -96,6 +96,7 @@ extern "C" int32_t zkb_init(int32_t device, zkb_ctx **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ZKB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ZKB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     *out = ctx;
     return ZKB_OK;
 }
@@ -115,6 +116,7 @@ extern "C" int32_t zkb_destroy(zkb_ctx *ctx) {
         if (b.ptr) cudaFree(b.ptr);
     for (auto &kv : ctx->block_cache) cudaFree(kv.second);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ZKB_OK;

@@ -340,6 +340,7 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
     std::unique_ptr<zkb_pk> pk(new zkb_pk());
     pk->ctx = ctx;
     pk->pool.ctx = ctx;
+    ZKB_TRY(zkb_csf_validate(csf, csf_words));
     if (!parse_csf(csf, csf_words, pk->cs)) return ZKB_ERR_ARG;
     const Csf &cs = pk->cs;
     ZKB_ARG((cs.nf == 0 || fixed_values) && (cs.perm.empty() || sigma_values));
@@ -448,6 +449,67 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
     return ZKB_OK;
 }
 
+// VerifyingKey::write(SerdeFormat::Processed) (halo2_proofs plonk.rs): u32 BE k || u32 BE num_fixed || fixed commitments ||
+// permutation commitments, points compressed -- the layout of the reference fixture's `vk` (aggregator/data/batch-task.json:
+// 0x19, 4, 4 + 3 points = 232 B).  Commitments = commit_lagrange of the fixed / sigma columns (keygen.rs), batched MSMs.
+extern "C" int32_t zkb_pk_vk_bytes(zkb_pk *pk, uint8_t *out, uint64_t cap, uint64_t *len) {
+    ZKB_ARG(pk && len);
+    const Csf &cs = pk->cs;
+    const uint64_t need = 8 + 32ull * (cs.nf + cs.perm.size());
+    *len = need;
+    if (!out) return ZKB_OK;
+    ZKB_ARG(cap >= need);
+    ZKB_CUDA(cudaSetDevice(pk->ctx->device));
+    cudaStream_t st = pk->ctx->stream;
+    std::vector<Fr *> cols;
+    for (auto c : pk->fixed_values) cols.push_back(c);
+    for (auto c : pk->sigma_values) cols.push_back(c);
+    std::vector<G1Affine> cms;
+    if (!cols.empty()) ZKB_TRY(commit_many(pk, cols, pk->g_lagrange, pk->n, cms, st));
+    auto be32 = [](uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; };
+    be32(out, cs.k);
+    be32(out + 4, cs.nf);
+    for (size_t i = 0; i < cms.size(); ++i) g1_compress(cms[i], out + 8 + 32 * i);
+    return ZKB_OK;
+}
+
+// host-only structural check of a CSF blob (no device needed)
+extern "C" int32_t zkb_csf_validate(const uint32_t *csf, uint64_t csf_words) {
+    ZKB_ARG(csf != nullptr);
+    Csf c;
+    if (!parse_csf(csf, csf_words, c)) return ZKB_ERR_ARG;
+    // node references must point backwards; column / challenge / constant indices must be in range
+    for (size_t i = 0; i < c.nodes.size(); ++i) {
+        const auto &nd = c.nodes[i];
+        bool ok = true;
+        switch (nd[0]) {
+        case N_CONST: ok = nd[1] < c.consts.size(); break;
+        case N_FIXED: ok = nd[1] < c.nf; break;
+        case N_ADVICE: ok = nd[1] < c.na; break;
+        case N_INSTANCE: ok = nd[1] < c.ni; break;
+        case N_CHALLENGE: ok = nd[1] < c.nch; break;
+        case N_NEG: ok = nd[1] < i; break;
+        case N_ADD: case N_MUL: ok = nd[1] < i && nd[2] < i; break;
+        case N_SCALED: ok = nd[1] < i && nd[2] < c.consts.size(); break;
+        }
+        if (!ok) { set_error("CSF: node %zu has an out-of-range operand", i); return ZKB_ERR_ARG; }
+    }
+    auto in_nodes = [&](uint32_t v) { return v < c.nodes.size(); };
+    for (auto g : c.gates) if (!in_nodes(g)) { set_error("CSF: gate references a missing node"); return ZKB_ERR_ARG; }
+    for (auto &lk : c.lookups) {
+        if (lk.inputs.empty() || lk.table.empty()) { set_error("CSF: empty lookup"); return ZKB_ERR_ARG; }
+        for (auto &inp : lk.inputs) for (auto v : inp) if (!in_nodes(v)) { set_error("CSF: lookup references a missing node"); return ZKB_ERR_ARG; }
+        for (auto v : lk.table) if (!in_nodes(v)) { set_error("CSF: lookup references a missing node"); return ZKB_ERR_ARG; }
+    }
+    for (auto &pc : c.perm) {
+        const uint32_t lim = pc[0] == N_FIXED ? c.nf : pc[0] == N_ADVICE ? c.na : pc[0] == N_INSTANCE ? c.ni : 0;
+        if (pc[1] >= lim) { set_error("CSF: permutation column out of range"); return ZKB_ERR_ARG; }
+    }
+    for (uint32_t ph : c.adv_phase) if (ph >= c.nphases) { set_error("CSF: advice phase out of range"); return ZKB_ERR_ARG; }
+    for (uint32_t ph : c.ch_phase) if (ph >= c.nphases) { set_error("CSF: challenge phase out of range"); return ZKB_ERR_ARG; }
+    return ZKB_OK;
+}
+
 extern "C" int32_t zkb_pk_destroy(zkb_pk *pk) {
     if (pk) {
         cudaSetDevice(pk->ctx->device);
@@ -501,17 +563,35 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
     ZKB_CUDA(cudaSetDevice(pk->ctx->device));
     cudaStream_t st = pk->ctx->stream;
     const uint64_t n = pk->n;
+    // H2D on the copy stream, batch by batch; the MSM of batch b waits only for batch b's event, so the copies of the
+    // following batches overlap it (pinned caller buffers; pageable ones are staged synchronously by the driver anyway)
     std::vector<Fr *> phase_cols;
+    std::vector<const uint64_t *> phase_src;
     for (uint32_t c = 0; c < cs.na; ++c) {
         if (cs.adv_phase[c] != phase) continue;
         ZKB_ARG(advice_columns[c] != nullptr);
         ZKB_TRY(s->pool.fr(n, &s->adv_values[c]));
-        ZKB_CUDA(cudaMemcpyAsync(s->adv_values[c], advice_columns[c], n * sizeof(Fr), cudaMemcpyHostToDevice, st));
         phase_cols.push_back(s->adv_values[c]);
+        phase_src.push_back(advice_columns[c]);
     }
-    std::vector<G1Affine> cms;
-    ZKB_TRY(commit_many(pk, phase_cols, pk->g_lagrange, n, cms, st));
-    for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
+    const uint32_t maxb = msm_max_batch(n);
+    const size_t nbatch = (phase_cols.size() + maxb - 1) / maxb;
+    std::vector<cudaEvent_t> evs(nbatch);
+    ZKB_CUDA(cudaStreamSynchronize(st));  // the destination blocks may still be in use by work queued on `st`
+    for (size_t b = 0; b < nbatch; ++b) {
+        ZKB_CUDA(cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming));
+        for (size_t i = b * maxb; i < std::min(phase_cols.size(), (b + 1) * (size_t)maxb); ++i)
+            ZKB_CUDA(cudaMemcpyAsync(phase_cols[i], phase_src[i], n * sizeof(Fr), cudaMemcpyHostToDevice, pk->ctx->copy_stream));
+        ZKB_CUDA(cudaEventRecord(evs[b], pk->ctx->copy_stream));
+    }
+    for (size_t b = 0; b < nbatch; ++b) {
+        ZKB_CUDA(cudaStreamWaitEvent(st, evs[b], 0));
+        std::vector<Fr *> part(phase_cols.begin() + b * maxb, phase_cols.begin() + std::min(phase_cols.size(), (b + 1) * (size_t)maxb));
+        std::vector<G1Affine> cms;
+        ZKB_TRY(commit_many(pk, part, pk->g_lagrange, n, cms, st));
+        for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
+    }
+    for (auto &e : evs) cudaEventDestroy(e);
     for (uint32_t i = 0; i < cs.nch; ++i) {
         if (cs.ch_phase[i] == phase) {
             s->challenges[i] = tr_squeeze(s);

@@ -51,6 +51,8 @@ SIGNATURES = {
     "zkb_g1_sum_affine_host": (ctypes.c_int32, [_vp, ctypes.c_uint64, _vp, _vp]),
     "zkb_pk_create": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "zkb_pk_destroy": (ctypes.c_int32, [_vp]),
+    "zkb_pk_vk_bytes": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
+    "zkb_csf_validate": (ctypes.c_int32, [_vp, ctypes.c_uint64]),
     "zkb_prove_begin": (ctypes.c_int32, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "zkb_prove_advice_phase": (ctypes.c_int32, [_vp, ctypes.c_uint32, _vp, _vp]),
     "zkb_prove_finish": (ctypes.c_int32, [_vp, _vp, _vp, _vp, _vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),

@@ -100,6 +100,13 @@ class ConstraintSystem:
         return np.array(w, dtype=np.uint32)
 
 
+def validate_csf(blob):
+    """host-only structural check of a CSF blob (raises ZkbError)."""
+    from .lib import load_library
+    b = np.ascontiguousarray(blob, dtype=np.uint32)
+    check(load_library().zkb_csf_validate(_vp(b.ctypes.data), b.size))
+
+
 def _ptr_array(arrs):
     """host numpy arrays (or None) -> (keepalive list, void** as c_void_p array)."""
     keep = [np.ascontiguousarray(a) if a is not None else None for a in arrs]
@@ -123,6 +130,14 @@ class ProvingKey:
         check(self.ctx.lib.zkb_pk_create(self.ctx.handle, _vp(blob.ctypes.data), blob.size, ctypes.cast(ftbl, _vp), ctypes.cast(stbl, _vp),
                                          _vp(g.ctypes.data), _vp(gl.ctypes.data), ctypes.byref(h)))
         self.handle = h
+
+    def vk_bytes(self):
+        """VerifyingKey::to_bytes(SerdeFormat::Processed): fixed + permutation commitments computed on the GPU."""
+        n = ctypes.c_uint64(0)
+        check(self.ctx.lib.zkb_pk_vk_bytes(self.handle, None, 0, ctypes.byref(n)))
+        out = (ctypes.c_uint8 * n.value)()
+        check(self.ctx.lib.zkb_pk_vk_bytes(self.handle, ctypes.cast(out, _vp), n.value, ctypes.byref(n)))
+        return bytes(out)
 
     def close(self):
         if self.handle:
