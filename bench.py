@@ -225,7 +225,9 @@ def main():
     achieved = (ALG_BYTES_PER_DIR / 2) / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one ntt_pass_kernel launch at 2^24 (ncu --set full capture
+                # profiles/r01_ntt_pass_v2_radix8_ncu.txt: 537.4 MB + 491.1 MB, average of the two passes); algorithmic 536.9 MB
+                "traffic": 1028.5e6,
                 "note": "kernel is integer-multiply-pipe bound (1 Montgomery mul = 139 IMAD.WIDE per butterfly), see DESIGN.md; "
                         "alg bytes/launch = 2*32*2^24/2 passes"}
 

@@ -130,6 +130,14 @@ ZKB_API int32_t zkb_ntt_cross_dev(zkb_ctx *ctx, const uint64_t *in_dev, uint64_t
                                   const uint64_t omega_p[4], void *stream);
 ZKB_API int32_t zkb_g1_sum_affine_host(const uint64_t *points, uint64_t count, uint64_t out_affine[8], uint8_t *out_compressed);
 
+/* zkb_comm_*   NCCL communicator of a context for the multi-GPU create_proof (one process per GPU).  Rank 0 creates a
+ * 128-byte unique id, the host layer broadcasts it, every rank calls zkb_comm_init.  With a communicator the proving session
+ * stays replicated (identical transcript and proof bytes on every rank) while commitment batches (column i -> rank i mod P) and
+ * the quotient's coset parts (part j -> rank j mod P) are dealt across the ranks and exchanged by one all-reduce each.        */
+ZKB_API int32_t zkb_comm_unique_id(uint8_t out[128]);
+ZKB_API int32_t zkb_comm_init(zkb_ctx *ctx, const uint8_t unique_id[128], int32_t rank, int32_t nranks);
+ZKB_API int32_t zkb_comm_destroy(zkb_ctx *ctx);
+
 /* ---- create_proof: device-resident proving session --------------------------------------------------------------
  * Replaces the body of halo2_proofs::plonk::create_proof::<KZGCommitmentScheme<Bn256>, ProverSHPLONK, Challenge255, R,
  * Blake2bWrite, C> (plonk/prover.rs; called at circuit-benchmarks/src/super_circuit.rs:117-132 and, through

@@ -60,6 +60,9 @@ struct zkb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of witness columns overlaps the MSMs of the previous batch
     int sm_count = 148;
+    // multi-GPU: NCCL communicator of this rank (comm.cu); nranks == 1 -> everything local
+    void *nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
     uint64_t launches = 0;
     uint64_t msm_last_adds = 0;
     std::map<std::array<uint64_t, 5>, zkb::NttPlan> ntt_plans;
@@ -108,6 +111,8 @@ int32_t prefix_sum_device(zkb_ctx *ctx, const Fr *in, uint64_t n, const Fr &init
 int32_t kate_division_device(zkb_ctx *ctx, const Fr *a, uint64_t n, const Fr &u, Fr *q, cudaStream_t st);
 int32_t lincomb_device(zkb_ctx *ctx, const Fr *const *d_polys, const Fr *d_coefs, uint32_t num, uint64_t n, Fr *out, bool accumulate, cudaStream_t st);
 int32_t batch_invert_device(zkb_ctx *ctx, const Fr *a, Fr *out, uint64_t n, cudaStream_t st);
+// in-place u64 sum across the context's ranks (exact gather when the supports are disjoint); no-op for a single rank
+int32_t comm_allreduce_u64(zkb_ctx *ctx, void *dev_buf, size_t count, cudaStream_t st);
 
-enum ScratchSlot { SCR_NTT = 0, SCR_MSM_A = 1, SCR_MSM_B = 2, SCR_MSM_C = 3, SCR_HOSTIO_A = 4, SCR_HOSTIO_B = 5, SCR_MISC = 6, SCR_MISC2 = 7, SCR_MSM_TBL = 8 };
+enum ScratchSlot { SCR_NTT = 0, SCR_MSM_A = 1, SCR_MSM_B = 2, SCR_MSM_C = 3, SCR_HOSTIO_A = 4, SCR_HOSTIO_B = 5, SCR_MISC = 6, SCR_MISC2 = 7, SCR_MSM_TBL = 8, SCR_COMM = 9 };
 }  // namespace zkb

@@ -104,6 +104,7 @@ extern "C" int32_t zkb_init(int32_t device, zkb_ctx **out) {
 extern "C" int32_t zkb_destroy(zkb_ctx *ctx) {
     if (!ctx) return ZKB_OK;
     cudaSetDevice(ctx->device);
+    zkb_comm_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->ntt_plans) {
         NttPlan &p = kv.second;

@@ -262,7 +262,7 @@ static int32_t commit(zkb_pk *pk, const Fr *scalars, const G1Affine *bases, uint
 }
 
 // commit several columns against the same bases with batched MSMs (one pass per <= msm_max_batch columns)
-static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Affine *bases, uint64_t len, std::vector<G1Affine> &out, cudaStream_t st) {
+static int32_t commit_many_local(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Affine *bases, uint64_t len, std::vector<G1Affine> &out, cudaStream_t st) {
     out.resize(cols.size());
     const uint32_t maxb = msm_max_batch(len);
     const G1Affine *shift = (bases == pk->g) ? pk->g_shift : (bases == pk->g_lagrange) ? pk->g_lagrange_shift : nullptr;
@@ -274,6 +274,27 @@ static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Af
         ZKB_CUDA(cudaMemcpyAsync(d_tbl, cols.data() + done, cur * sizeof(Fr *), cudaMemcpyHostToDevice, st));
         ZKB_TRY(msm_g1_batch_device_ex(pk->ctx, d_tbl, cur, shift ? shift : bases, len, out.data() + done, shift != nullptr, st));
     }
+    return ZKB_OK;
+}
+// commit several columns against the same bases with batched MSMs.  With a communicator, column i is committed by rank
+// i mod P and the 64-byte results are exchanged by one all-reduce (u64 sum of disjoint supports = gather).
+static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Affine *bases, uint64_t len, std::vector<G1Affine> &out, cudaStream_t st) {
+    zkb_ctx *ctx = pk->ctx;
+    if (ctx->nranks <= 1 || cols.size() < 2) return commit_many_local(pk, cols, bases, len, out, st);
+    std::vector<Fr *> mine;
+    std::vector<size_t> mine_idx;
+    for (size_t i = 0; i < cols.size(); ++i)
+        if ((int)(i % ctx->nranks) == ctx->rank) { mine.push_back(cols[i]); mine_idx.push_back(i); }
+    std::vector<G1Affine> part;
+    if (!mine.empty()) ZKB_TRY(commit_many_local(pk, mine, bases, len, part, st));
+    out.assign(cols.size(), G1Affine{Fq::zero(), Fq::zero()});
+    for (size_t t = 0; t < mine_idx.size(); ++t) out[mine_idx[t]] = part[t];
+    G1Affine *d_buf = nullptr;
+    ZKB_TRY(scratch_get(ctx, SCR_COMM, cols.size() * sizeof(G1Affine), (void **)&d_buf));
+    ZKB_CUDA(cudaMemcpyAsync(d_buf, out.data(), cols.size() * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
+    ZKB_TRY(comm_allreduce_u64(ctx, d_buf, cols.size() * 8, st));
+    ZKB_CUDA(cudaMemcpyAsync(out.data(), d_buf, cols.size() * sizeof(G1Affine), cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaStreamSynchronize(st));
     return ZKB_OK;
 }
 
@@ -1003,7 +1024,9 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     ZKB_TRY(pool.alloc(qcols.size() * sizeof(Fr *) + 8, (void **)&d_qcols));
     std::vector<Fr *> hout{h_ext};
     ZKB_TRY(upload_table(pool, hout, &d_hout, st));
+    if (ctx->nranks > 1) ZKB_CUDA(cudaMemsetAsync(h_ext, 0, pk->N * sizeof(Fr), st));
     for (uint32_t j = 0; j < pk->E; ++j) {
+        if (ctx->nranks > 1 && (int)(j % ctx->nranks) != ctx->rank) continue;  // coset part j belongs to rank j mod P
         const Fr gj = fp_mul(pk->zeta, fp_pow_u64(pk->ext_omega, j));
         ZKB_TRY(fr_powers_device(ctx, gj, n, pows, st));
         ZKB_TRY(ntt_many(ntt_src, ntt_dst, pk->omega, nullptr, pows));
@@ -1017,6 +1040,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, pk->E, j, st));
         ZKB_CUDA(cudaStreamSynchronize(st));  // `tail` and `cols_j` live on the stack
     }
+    ZKB_TRY(comm_allreduce_u64(ctx, h_ext, pk->N * 4, st));  // gather the coset parts of the other ranks (no-op on one GPU)
     trace.mark("quotient: coset NTTs + fused eval");
     // extended_to_coeff: inverse NTT over the extended domain, 1/N, undo the zeta coset, keep n*(d-1) coefficients
     ZKB_TRY(ntt_fr_device(ctx, h_ext, h_ext, pk->ext_k, pk->ext_omega_inv, &pk->N_inv, 2, nullptr, st));

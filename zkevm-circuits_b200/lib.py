@@ -49,6 +49,9 @@ SIGNATURES = {
     "zkb_kate_division_dev": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "zkb_ntt_cross_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint64, _vp, _vp]),
     "zkb_g1_sum_affine_host": (ctypes.c_int32, [_vp, ctypes.c_uint64, _vp, _vp]),
+    "zkb_comm_unique_id": (ctypes.c_int32, [_vp]),
+    "zkb_comm_init": (ctypes.c_int32, [_vp, _vp, ctypes.c_int32, ctypes.c_int32]),
+    "zkb_comm_destroy": (ctypes.c_int32, [_vp]),
     "zkb_pk_create": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "zkb_pk_destroy": (ctypes.c_int32, [_vp]),
     "zkb_pk_vk_bytes": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
@@ -106,6 +109,22 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def init_comm(self, group=None):
+        """Create this rank's NCCL communicator (multi-GPU create_proof): rank 0's unique id is broadcast with torch.distributed."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (ctypes.c_uint8 * 128)()
+        if rank == 0:
+            check(self.lib.zkb_comm_unique_id(ctypes.cast(buf, _vp)))
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        buf2 = (ctypes.c_uint8 * 128).from_buffer_copy(raw)
+        check(self.lib.zkb_comm_init(self.handle, ctypes.cast(buf2, _vp), rank, world))
+        return rank, world
 
     @property
     def launch_count(self):
