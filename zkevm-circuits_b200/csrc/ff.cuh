@@ -401,6 +401,22 @@ FF_D Fp<PR> fp_load(const Fp<PR> *p) {
     r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
     return r;
 }
+// streaming variants: bypass L1 (ld.global.cg / st.global.cg) so one-touch data does not evict the L1-resident twiddle tables
+template <class PR>
+FF_D Fp<PR> fp_load_stream(const Fp<PR> *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+    Fp<PR> r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+template <class PR>
+FF_D void fp_store_stream(Fp<PR> *p, const Fp<PR> &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    __stcg(q, make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]));
+    __stcg(q + 1, make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]));
+}
 template <class PR>
 FF_D void fp_store(Fp<PR> *p, const Fp<PR> &v) {
     uint4 *q = reinterpret_cast<uint4 *>(p);

@@ -119,15 +119,28 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const Fr *__restrict__ in
     const uint64_t j_in = sub & ((1ull << p.log_inner) - 1);
     const uint64_t base = (outer << (p.a + p.log_inner)) + j_in;
 
-    for (uint32_t j = tid; j < A; j += nt) {
-        const uint64_t idx = base + ((uint64_t)j << p.log_inner);
-        Fr v = fp_load(in + idx);
-        if (p.coset_in) {
-            const uint32_t m = (uint32_t)(idx % 3);
-            if (m) v = fp_mul(v, zeta_pow(m));
+    // load phase: 4 independent 32-byte loads in flight per thread before anything is consumed
+    for (uint32_t j0 = tid; j0 < A; j0 += 4 * nt) {
+        Fr v[4];
+        uint64_t idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t j = j0 + u * nt;
+            idx[u] = base + ((uint64_t)j << p.log_inner);
+            if (j < A) v[u] = fp_load_stream(in + idx[u]);
         }
-        if (p.in_scale) v = fp_mul(v, fp_load(p.in_scale + idx));
-        smem_st(lo, hi, j, v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t j = j0 + u * nt;
+            if (j < A) {
+                if (p.coset_in) {
+                    const uint32_t m = (uint32_t)(idx[u] % 3);
+                    if (m) v[u] = fp_mul(v[u], zeta_pow(m));
+                }
+                if (p.in_scale) v[u] = fp_mul(v[u], fp_load(p.in_scale + idx[u]));
+                smem_st(lo, hi, j, v[u]);
+            }
+        }
     }
     __syncthreads();
 
@@ -139,27 +152,47 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const Fr *__restrict__ in
         else if (p.a - s == 1) { ntt_round<1>(lo, hi, p.a, s, p.loc, tid, nt); __syncthreads(); }
     }
 
-    for (uint32_t q = tid; q < A; q += nt) {
-        const uint32_t k = p.a ? (__brev(q) >> (32 - p.a)) : 0;
-        Fr v = smem_ld(lo, hi, q);
-        uint64_t oidx;
-        if (p.is_final) {
-            const uint64_t k1 = p.a2 ? (outer >> p.a2) : outer;
-            const uint64_t k2 = p.a2 ? (outer & ((1ull << p.a2) - 1)) : 0;
-            oidx = (p.a1 ? k1 : 0) + (k2 << p.a1) + ((uint64_t)k << (p.a1 + p.a2));
+    if (p.is_final) {
+        const uint64_t k1 = p.a2 ? (outer >> p.a2) : outer;
+        const uint64_t k2 = p.a2 ? (outer & ((1ull << p.a2) - 1)) : 0;
+        const uint64_t obase = (p.a1 ? k1 : 0) + (k2 << p.a1);
+        for (uint32_t q = tid; q < A; q += nt) {
+            const uint32_t k = p.a ? (__brev(q) >> (32 - p.a)) : 0;
+            Fr v = smem_ld(lo, hi, q);
+            const uint64_t oidx = obase + ((uint64_t)k << (p.a1 + p.a2));
             if (p.use_scale) v = fp_mul(v, fp_load(p.scale));
             if (p.coset_out) {
                 const uint32_t m = (uint32_t)(oidx % 3);
                 if (m) v = fp_mul(v, zeta_pow(3 - m));  // ZETA^(-m) = ZETA^(3-m)
             }
-        } else {
-            const uint64_t e = (j_in * (uint64_t)k) << p.tw_shift;
-            Fr tw = fp_load(p.tw_lo + (e & ((1u << TW_LO_BITS) - 1)));
-            if (p.log_n > TW_LO_BITS) tw = fp_mul(tw, fp_load(p.tw_hi + (e >> TW_LO_BITS)));
-            v = fp_mul(v, tw);
-            oidx = base + ((uint64_t)k << p.log_inner);
+            fp_store_stream(out + oidx, v);
         }
-        fp_store(out + oidx, v);
+    } else {
+        // inter-pass twiddle w_n^(j_in * k) = lo[e & 4095] * hi[e >> 12]: the table reads of two elements are issued together
+        const bool two_level = p.log_n > TW_LO_BITS;
+        for (uint32_t q0 = tid; q0 < A; q0 += 2 * nt) {
+            uint32_t k[2];
+            Fr tl[2], th[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t q = q0 + u * nt;
+                k[u] = __brev(q) >> (32 - p.a);
+                if (q < A) {
+                    const uint64_t e = (j_in * (uint64_t)k[u]) << p.tw_shift;
+                    tl[u] = fp_load(p.tw_lo + (e & ((1u << TW_LO_BITS) - 1)));
+                    if (two_level) th[u] = fp_load(p.tw_hi + (e >> TW_LO_BITS));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t q = q0 + u * nt;
+                if (q < A) {
+                    Fr tw = two_level ? fp_mul(tl[u], th[u]) : tl[u];
+                    const Fr v = fp_mul(smem_ld(lo, hi, q), tw);
+                    fp_store_stream(out + base + ((uint64_t)k[u] << p.log_inner), v);
+                }
+            }
+        }
     }
 }
 
