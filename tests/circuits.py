@@ -135,3 +135,100 @@ class ToyCircuit:
             if self.fixed_ints[0][i]:
                 self.cols0[2][i] = (self.cols0[2][i] + 1) % R
                 return
+
+
+class ThinCompressionShape:
+    """The constraint system of the reference's thin compression circuit exactly as its snark-verifier `Protocol` spells it
+    (aggregator/data/batch-task.json -> chunk_proofs[0].protocol), at a small k with a synthetic witness:
+      fixed: 0 lookup table, 1 constants column, 2 gate selector, 3 lookup selector;  advice: 0;  instance: 0
+      gate  : q_gate * (a(0) + a(1) * a(2) - a(3))            (halo2-lib flex gate)
+      lookup: (q_lookup * a(0)) in table                       (one input set, one table column)
+      permutation over [fixed 1, advice 0, instance 0]         (one chunk: cs degree 5 -> chunk length 3)
+    Expected proof layout (fixture): 1 advice + 1 m + z, phi, random + 4 h pieces + 17 evals + 2 = 28 items."""
+
+    def __init__(self, k, seed=0, n_instance=6):
+        rnd = random.Random(seed)
+        self.k, self.n = k, 1 << k
+        n = self.n
+        cs = H.ConstraintSystem(k, 4, 1, 1)
+        a = lambda r=0: H.advice(0, r)
+        cs.gates.append(H.fixed(2) * (a(0) + a(1) * a(2) - a(3)))
+        cs.lookups.append(H.Lookup([[H.fixed(3) * a(0)]], [H.fixed(0)]))
+        cs.perm_columns = [(FIXED, 1), (ADVICE, 0), (INSTANCE, 0)]
+        cs.finalize()
+        # the fixture's evaluation order lists fixed column 1 (constants, from the permutation) before column 0: halo2 records
+        # queries in configure() order (enable_equality on the constants column happens before the lookup table is queried)
+        cs.fixed_queries = [(1, 0), (0, 0), (2, 0), (3, 0)]
+        self.cs = cs
+        bf = cs.blinding_factors()
+        assert bf == 6 and cs.degree() == 5
+        usable = n - (bf + 1)
+        self.usable = usable
+        T = 1 << max(2, k - 2)
+        fixed = [[0] * n for _ in range(4)]
+        for j in range(T): fixed[0][j] = j
+        self.instances = [[rnd.randrange(R) for _ in range(n_instance)]]
+        A = [rnd.randrange(T) for _ in range(n)]          # default: small values (valid lookup inputs)
+        copies = []
+        r = 0
+        while r + 4 <= usable:
+            kind = rnd.random()
+            if kind < 0.5:                                 # a gate instance on rows r..r+3
+                fixed[2][r] = 1
+                A[r], A[r + 1], A[r + 2] = rnd.randrange(R), rnd.randrange(R), rnd.randrange(R)
+                if kind < 0.1 and n_instance:
+                    j = rnd.randrange(n_instance); A[r] = self.instances[0][j]; copies.append(((ADVICE, 0, r), (INSTANCE, 0, j)))
+                elif kind < 0.2:
+                    c = rnd.randrange(R); fixed[1][r] = c; A[r] = c; copies.append(((ADVICE, 0, r), (FIXED, 1, r)))
+                A[r + 3] = (A[r] + A[r + 1] * A[r + 2]) % R
+                r += 4
+            else:                                          # a range-checked cell
+                fixed[3][r] = 1
+                A[r] = rnd.randrange(T)
+                r += 1
+        for _ in range(usable // 8):
+            i, j = rnd.randrange(usable), rnd.randrange(usable)
+            if A[i] == A[j]: copies.append(((ADVICE, 0, i), (ADVICE, 0, j)))
+        self.fixed_ints, self.copies, self.A = fixed, copies, A
+        self.bf = bf
+        self.blind = [rnd.randrange(R) for _ in range(bf + 1)]
+        self.blinds_ints = {"z": [[rnd.randrange(R) for _ in range(bf)]], "phi": [[rnd.randrange(R) for _ in range(bf)]],
+                            "random_poly": [rnd.randrange(R) for _ in range(n)]}
+        self.transcript_repr = rnd.randrange(R)
+
+    def advice_ints(self, phase, challenges):
+        v = list(self.A)
+        v[self.usable:] = self.blind
+        return {0: v}
+
+
+class GatesOnlyCircuit:
+    """No permutation, no lookup, no instance: one fixed selector, two advice columns, one degree-3 gate with rotations."""
+
+    def __init__(self, k, seed=0):
+        rnd = random.Random(seed)
+        self.k, self.n = k, 1 << k
+        n = self.n
+        cs = H.ConstraintSystem(k, 1, 2, 0)
+        cs.gates.append(H.fixed(0) * (H.advice(0) * H.advice(1, 1) - H.advice(1, -1)))
+        cs.finalize()
+        self.cs = cs
+        bf = cs.blinding_factors()
+        usable = n - (bf + 1)
+        self.usable = usable
+        q = [1 if 0 < i < usable - 1 and i % 2 == 1 else 0 for i in range(n)]
+        a0 = [rnd.randrange(R) for _ in range(n)]
+        a1 = [rnd.randrange(R) for _ in range(n)]
+        for i in range(n - 1, -1, -1):                            # descending: a1[i+1] is final when a1[i-1] is derived
+            if q[i]: a1[i - 1] = a0[i] * a1[i + 1] % R           # odd rows constrain their even neighbours
+        self.fixed_ints, self.copies, self.instances = [q], [], []
+        self.cols = [a0, a1]
+        self.blind_rows = [[rnd.randrange(R) for _ in range(bf + 1)] for _ in range(2)]
+        self.blinds_ints = {"z": [], "phi": [], "random_poly": [rnd.randrange(R) for _ in range(n)]}
+        self.transcript_repr = rnd.randrange(R)
+
+    def advice_ints(self, phase, challenges):
+        out = {}
+        for c in range(2):
+            v = list(self.cols[c]); v[self.usable:] = self.blind_rows[c]; out[c] = v
+        return out

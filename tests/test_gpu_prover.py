@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import halo2_ref as H
-from circuits import ToyCircuit
+from circuits import ToyCircuit, ThinCompressionShape, GatesOnlyCircuit
 
 pytestmark = pytest.mark.gpu
 
@@ -39,10 +39,14 @@ def first_diff(a, b):
     return None if len(a) == len(b) else min(len(a), len(b)) // 32
 
 
-@pytest.mark.parametrize("k,kw", [(5, {}), (6, dict(two_phase=False)), (6, dict(lookups=False, extra_perm=False)), (8, {}), (11, {})])
-def test_create_proof_matches_oracle(k, kw):
+CASES = [("toy", 5, {}), ("toy", 6, dict(two_phase=False)), ("toy", 6, dict(lookups=False, extra_perm=False)), ("toy", 8, {}), ("toy", 11, {}),
+         ("thin", 7, {}), ("thin", 10, {}), ("gates", 5, {}), ("gates", 9, {})]
+
+
+@pytest.mark.parametrize("kind,k,kw", CASES)
+def test_create_proof_matches_oracle(kind, k, kw):
     from zkb200 import plonk as Z
-    tc = ToyCircuit(k, seed=100 + k, **kw)
+    tc = {"toy": ToyCircuit, "thin": ThinCompressionShape, "gates": GatesOnlyCircuit}[kind](k, seed=100 + k, **kw)
     ref = H.Ref(tc.cs, 1234)
     F = ref.F
     fixed = [F.arr(c) for c in tc.fixed_ints]

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import halo2_ref as H
-from circuits import ToyCircuit
+from circuits import ToyCircuit, ThinCompressionShape, GatesOnlyCircuit
 
 
 def prove(tc, srs_s=1234):
@@ -54,3 +54,32 @@ def test_reject_unsatisfied_witness():
     tc.tamper()
     ref, pk, proof, _ = prove(tc)
     assert not ref.verify_proof(pk, tc.transcript_repr, tc.instances, proof)
+
+
+def test_thin_compression_shape_matches_fixture_layout(golden):
+    """Prove the reference's thin compression constraint system (from the fixture's Protocol) on a synthetic witness: the proof
+    must have the fixture's layout -- 28 items: 1 advice, 1 m, z, phi, random, 4 h pieces, 17 evaluations, 2 opening points --
+    and the evaluation order recorded in the fixture."""
+    tc = ThinCompressionShape(7, seed=5)
+    ref, pk, proof, dbg = prove(tc)
+    assert ref.verify_proof(pk, tc.transcript_repr, tc.instances, proof)
+    assert len(proof) == len(bytes.fromhex(golden["proof_hex"])) == 28 * 32
+    assert ref.dom.qdeg == golden["quotient_num_chunk"] and ref.bf == 6
+    # evaluation order: snark-verifier polynomial numbering p0-p3 fixed (table, constants, q_gate, q_lookup), p4-p6 sigma,
+    # p8 advice, p9 m, p10 z, p11 phi, p12 random
+    cs = tc.cs
+    order = [(8, r) for (_, r) in cs.advice_queries] + [(c, r) for (c, r) in cs.fixed_queries] + [(12, 0)] + [(4, 0), (5, 0), (6, 0)] \
+        + [(10, 0), (10, 1)] + [(11, 0), (11, 1), (9, 0)]
+    assert order == [(e["poly"], e["rotation"]) for e in golden["evaluations"]]
+    # commitments / evaluations decode as points / canonical scalars at the fixture's positions
+    import pyref as P
+    for i in list(range(9)) + [26, 27]:
+        assert P.g1_is_on_curve(P.g1_decompress(proof[32 * i: 32 * i + 32]))
+    for i in range(9, 26):
+        assert int.from_bytes(proof[32 * i: 32 * i + 32], "little") < P.R_MOD
+
+
+def test_gates_only_circuit():
+    tc = GatesOnlyCircuit(5, seed=9)
+    ref, pk, proof, _ = prove(tc)
+    assert ref.verify_proof(pk, tc.transcript_repr, tc.instances, proof)
