@@ -124,8 +124,35 @@ API void zko_best_fft(uint64_t *data, const uint64_t omega[4], uint32_t log_n) {
             for (uint64_t i = s; i < e; ++i) { tw[i] = cur; fe_mul(&cur, &cur, &w, FR); }
         }
     }
-    uint64_t chunk = 2, twiddle_chunk = half;
-    for (uint32_t layer = 0; layer < log_n; ++layer) {
+    /* layers: same butterflies as upstream; scheduled cache-blocked -- the first `local` layers only mix elements inside
+     * blocks of 2^local entries, so each block runs them back to back while it is cache resident (one thread per block);
+     * the remaining layers are data-parallel sweeps.  The arithmetic per butterfly is unchanged. */
+    uint32_t local = log_n < 14 ? log_n : 14;
+    if (n >> local < (uint64_t)zko_num_threads()) local = 0;   /* too few blocks to keep all threads busy */
+    if (local) {
+        const uint64_t bsz = 1ULL << local;
+#pragma omp parallel for schedule(static)
+        for (int64_t b = 0; b < (int64_t)(n >> local); ++b) {
+            fe_t *blk = a + (uint64_t)b * bsz;
+            uint64_t chunk = 2, twiddle_chunk = half;
+            for (uint32_t layer = 0; layer < local; ++layer) {
+                const uint64_t hc = chunk / 2;
+                for (uint64_t s0 = 0; s0 < bsz; s0 += chunk) {
+                    for (uint64_t i = 0; i < hc; ++i) {
+                        fe_t *lo = &blk[s0 + i], *hi = lo + hc;
+                        fe_t t;
+                        if (i == 0) t = *hi; else fe_mul(&t, hi, &tw[i * twiddle_chunk], FR);
+                        fe_sub(hi, lo, &t, FR);
+                        fe_add(lo, lo, &t, FR);
+                    }
+                }
+                chunk *= 2;
+                twiddle_chunk /= 2;
+            }
+        }
+    }
+    uint64_t chunk = 2ULL << local, twiddle_chunk = half >> local;
+    for (uint32_t layer = local; layer < log_n; ++layer) {
         const uint64_t hc = chunk / 2;
 #pragma omp parallel for schedule(static)
         for (int64_t idx = 0; idx < (int64_t)half; ++idx) {

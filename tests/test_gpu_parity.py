@@ -197,3 +197,45 @@ def test_msm_batch_vs_single(A, oracle):
     got = A.best_multiexp_batch_dev(many, bt)
     for i in (0, 33, 69):
         assert (got[i] == A.best_multiexp_dev(many[i], bt).affine).all()
+
+
+@pytest.mark.parametrize("k,j", [(6, 3), (9, 5), (11, 9)])
+def test_evaluation_domain_vs_oracle(oracle, k, j):
+    """EvaluationDomain::{lagrange_to_coeff, coeff_to_extended, extended_to_coeff} mirror vs the oracle's restatement."""
+    import halo2_ref as H
+    from zkb200.domain import EvaluationDomain
+    ref = H.Ref(H.ConstraintSystem(k, 0, 1, 0).finalize(), 99)
+    ref.dom = H.Domain(k, j)
+    dom = EvaluationDomain(j, k)
+    assert dom.extended_k == ref.dom.extended_k
+    a = rand_field(1 << k, 31 + k)
+    coeff = dom.lagrange_to_coeff(to_dev(a))
+    assert (to_host(coeff) == ref.lagrange_to_coeff(a)).all()
+    ext = dom.coeff_to_extended(coeff)
+    assert (to_host(ext) == ref.coeff_to_extended(to_host(coeff))).all()
+    back = dom.extended_to_coeff(ext)
+    exp = ref.extended_to_coeff(to_host(ext))
+    assert (to_host(back) == exp).all()
+    assert (to_host(back)[: 1 << k] == to_host(coeff)).all() and not to_host(back)[1 << k:].any()
+
+
+def test_msm_2_23_linearity(A, oracle):
+    """BASELINE config #5 shard size (2^26 / 8 GPUs = 2^23 points per GPU): size-independent property
+    MSM(a + b) == MSM(a) + MSM(b), plus MSM(0) == identity and a spot value from a sparse scalar vector."""
+    import torch
+    from zkb200 import parallel
+    n = 1 << 23
+    bases = A.g1_fixed_base_mul_dev(oracle.g1_generator(), A.random_fr_dev(n, 5150))
+    a, b = A.random_fr_dev(n, 1), A.random_fr_dev(n, 2)
+    ra, rb = A.best_multiexp_dev(a, bases), A.best_multiexp_dev(b, bases)
+    rab = A.best_multiexp_dev(A.field_binop_dev(0, 0, a, b), bases)
+    s, comp = parallel.g1_sum_affine(np.stack([ra.affine, rb.affine]))
+    assert (rab.affine == s).all() and rab.compressed == comp
+    assert oracle.g1_is_on_curve(rab.affine)
+    sparse = torch.zeros_like(a)
+    idx = [3, 77777, n - 1]
+    for i in idx: sparse[i] = a[i]
+    r = A.best_multiexp_dev(sparse, bases)
+    hb, ha = to_host(bases), to_host(a)
+    exp = oracle.g1_to_affine(oracle.best_multiexp(np.stack([ha[i] for i in idx]), np.stack([hb[i] for i in idx])))
+    assert (r.affine == exp).all()
