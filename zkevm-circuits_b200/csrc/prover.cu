@@ -298,6 +298,13 @@ static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Af
     return ZKB_OK;
 }
 
+// multi-GPU dealing of independent units: unit i of `count` is computed by rank i mod P (everything local on one GPU or when
+// there is a single unit); results are written into a zero-initialised slab and gathered by one all-reduce
+static inline bool unit_owned(const zkb_ctx *ctx, size_t i, size_t count) {
+    return ctx->nranks <= 1 || count < 2 || (int)(i % ctx->nranks) == ctx->rank;
+}
+static inline bool units_dealt(const zkb_ctx *ctx, size_t count) { return ctx->nranks > 1 && count >= 2; }
+
 // program bundle uploaded to the device
 struct DeviceProgram {
     Instr *code = nullptr;
@@ -585,34 +592,45 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
     cudaStream_t st = pk->ctx->stream;
     const uint64_t n = pk->n;
     // H2D on the copy stream, batch by batch; the MSM of batch b waits only for batch b's event, so the copies of the
-    // following batches overlap it (pinned caller buffers; pageable ones are staged synchronously by the driver anyway)
-    std::vector<Fr *> phase_cols;
+    // following batches overlap it (pinned caller buffers; pageable ones are staged synchronously by the driver anyway).
+    // Multi-GPU: a rank uploads and commits only the columns it owns, then the column data is gathered over NVLink.
     std::vector<const uint64_t *> phase_src;
+    std::vector<uint32_t> phase_idx;
     for (uint32_t c = 0; c < cs.na; ++c) {
         if (cs.adv_phase[c] != phase) continue;
         ZKB_ARG(advice_columns[c] != nullptr);
-        ZKB_TRY(s->pool.fr(n, &s->adv_values[c]));
-        phase_cols.push_back(s->adv_values[c]);
         phase_src.push_back(advice_columns[c]);
+        phase_idx.push_back(c);
     }
+    const size_t ncols = phase_src.size();
+    Fr *slab = nullptr;
+    ZKB_TRY(s->pool.fr(ncols * n, &slab));
+    std::vector<Fr *> phase_cols(ncols);
+    for (size_t i = 0; i < ncols; ++i) { phase_cols[i] = slab + i * n; s->adv_values[phase_idx[i]] = phase_cols[i]; }
+    const bool dealt = units_dealt(pk->ctx, ncols);
+    ZKB_CUDA(cudaStreamSynchronize(st));  // the destination block may still be in use by work queued on `st`
+    if (dealt) ZKB_CUDA(cudaMemsetAsync(slab, 0, ncols * n * sizeof(Fr), pk->ctx->copy_stream));
     const uint32_t maxb = msm_max_batch(n);
-    const size_t nbatch = (phase_cols.size() + maxb - 1) / maxb;
+    const size_t nbatch = dealt ? 1 : (ncols + maxb - 1) / maxb;
     std::vector<cudaEvent_t> evs(nbatch);
-    ZKB_CUDA(cudaStreamSynchronize(st));  // the destination blocks may still be in use by work queued on `st`
     for (size_t b = 0; b < nbatch; ++b) {
         ZKB_CUDA(cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming));
-        for (size_t i = b * maxb; i < std::min(phase_cols.size(), (b + 1) * (size_t)maxb); ++i)
-            ZKB_CUDA(cudaMemcpyAsync(phase_cols[i], phase_src[i], n * sizeof(Fr), cudaMemcpyHostToDevice, pk->ctx->copy_stream));
+        const size_t lo = dealt ? 0 : b * maxb, hi = dealt ? ncols : std::min(ncols, (b + 1) * (size_t)maxb);
+        for (size_t i = lo; i < hi; ++i)
+            if (unit_owned(pk->ctx, i, ncols))
+                ZKB_CUDA(cudaMemcpyAsync(phase_cols[i], phase_src[i], n * sizeof(Fr), cudaMemcpyHostToDevice, pk->ctx->copy_stream));
         ZKB_CUDA(cudaEventRecord(evs[b], pk->ctx->copy_stream));
     }
     for (size_t b = 0; b < nbatch; ++b) {
         ZKB_CUDA(cudaStreamWaitEvent(st, evs[b], 0));
-        std::vector<Fr *> part(phase_cols.begin() + b * maxb, phase_cols.begin() + std::min(phase_cols.size(), (b + 1) * (size_t)maxb));
+        const size_t lo = dealt ? 0 : b * maxb, hi = dealt ? ncols : std::min(ncols, (b + 1) * (size_t)maxb);
+        std::vector<Fr *> part(phase_cols.begin() + lo, phase_cols.begin() + hi);
         std::vector<G1Affine> cms;
-        ZKB_TRY(commit_many(pk, part, pk->g_lagrange, n, cms, st));
+        ZKB_TRY(commit_many(pk, part, pk->g_lagrange, n, cms, st));   // dealt: column i of the phase -> rank i mod P
         for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
     }
     for (auto &e : evs) cudaEventDestroy(e);
+    if (dealt) ZKB_TRY(comm_allreduce_u64(pk->ctx, slab, ncols * n * 4, st));
     for (uint32_t i = 0; i < cs.nch; ++i) {
         if (cs.ch_phase[i] == phase) {
             s->challenges[i] = tr_squeeze(s);
@@ -695,7 +713,17 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
 
     std::vector<std::vector<Fr *>> lk_f(nl);   // compressed inputs per lookup / input set
     std::vector<Fr *> lk_t(nl), lk_m(nl);
+    // multi-GPU: lookup argument l is prepared by rank l mod P; m columns live in one slab (+ one word carrying error counts)
+    const bool lk_dealt = units_dealt(ctx, nl);
+    Fr *m_slab = nullptr;
+    if (nl) {
+        ZKB_TRY(pool.fr(nl * n + 1, &m_slab));
+        if (lk_dealt) ZKB_CUDA(cudaMemsetAsync(m_slab, 0, (nl * n + 1) * sizeof(Fr), st));
+        for (size_t l = 0; l < nl; ++l) lk_m[l] = m_slab + l * n;
+    }
+    uint64_t lookup_errors = 0;
     for (size_t l = 0; l < nl; ++l) {
+        if (!unit_owned(ctx, l, nl)) continue;
         const CsfLookup &lk = cs.lookups[l];
         ExprBuilder eb;
         ProgramBuilder pb(eb);
@@ -731,13 +759,27 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         const unsigned ub = (usable + 255) / 256;
         m_insert_kernel<<<ub, 256, 0, st>>>(lk_t[l], usable, slots, tsize - 1);
         for (size_t j = 0; j < lk.inputs.size(); ++j) m_count_kernel<<<ub, 256, 0, st>>>(lk_f[l][j], lk_t[l], usable, slots, tsize - 1, counts, d_err);
-        ZKB_TRY(pool.fr(n, &lk_m[l]));
         counts_to_fr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts, (uint32_t)n, lk_m[l]);
         ctx->launches += 2 + lk.inputs.size();
         int herr = 0;
         ZKB_CUDA(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
         ZKB_CUDA(cudaStreamSynchronize(st));
-        if (herr) { set_error("lookup %zu: an input row is not in the table (unsatisfied witness)", l); return ZKB_ERR_ARG; }
+        if (herr) {
+            set_error("lookup %zu: an input row is not in the table (unsatisfied witness)", l);
+            if (!lk_dealt) return ZKB_ERR_ARG;
+            lookup_errors++;   // multi-GPU: every rank must learn about it before anyone leaves the collective sequence
+        }
+    }
+    if (lk_dealt) {
+        ZKB_CUDA(cudaMemcpyAsync(m_slab + nl * n, &lookup_errors, 8, cudaMemcpyHostToDevice, st));
+        ZKB_TRY(comm_allreduce_u64(ctx, m_slab, (nl * n + 1) * 4, st));
+        uint64_t total_err = 0;
+        ZKB_CUDA(cudaMemcpyAsync(&total_err, m_slab + nl * n, 8, cudaMemcpyDeviceToHost, st));
+        ZKB_CUDA(cudaStreamSynchronize(st));
+        if (total_err) {
+            if (!lookup_errors) set_error("a lookup input row is not in the table (reported by another rank)");
+            return ZKB_ERR_ARG;
+        }
     }
     {
         std::vector<G1Affine> cms;
@@ -806,7 +848,14 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     trace.mark("permutation z + commit");
     // ---------------------------------------------------------------- lookup grand sums phi
     std::vector<Fr *> phis(nl);
+    Fr *phi_slab = nullptr;
+    if (nl) {
+        ZKB_TRY(pool.fr(nl * n, &phi_slab));
+        if (lk_dealt) ZKB_CUDA(cudaMemsetAsync(phi_slab, 0, nl * n * sizeof(Fr), st));
+        for (size_t l = 0; l < nl; ++l) phis[l] = phi_slab + l * n;
+    }
     for (size_t l = 0; l < nl; ++l) {
+        if (!unit_owned(ctx, l, nl)) continue;
         const size_t J = lk_f[l].size();
         // denominators (f_j + beta), (t + beta) into one contiguous array, inverted at once
         Fr *dens, *invs, *dterm;
@@ -850,10 +899,10 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
             ZKB_TRY(upload_table(pool, outs, &d_outs, st));
             ZKB_TRY(expr_run_device(ctx, dp.code, dp.ncode, dp.nregs, d_cols, dp.consts, d_outs, k, 1, 0, st));
         }
-        ZKB_TRY(pool.fr(n, &phis[l]));
         ZKB_TRY(prefix_sum_device(ctx, dterm, n, Fr::zero(), phis[l], st));
         ZKB_CUDA(cudaMemcpyAsync(phis[l] + (n - bf), phi_blinds + 4ull * bf * l, (size_t)bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
     }
+    if (lk_dealt) ZKB_TRY(comm_allreduce_u64(ctx, phi_slab, nl * n * 4, st));
     {
         std::vector<G1Affine> cms;
         ZKB_TRY(commit_many(pk, phis, pk->g_lagrange, n, cms, st));
@@ -888,9 +937,18 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     };
     auto to_coeff_new = [&](const std::vector<Fr *> &vals, std::vector<Fr *> &polys) -> int32_t {
         polys.resize(vals.size());
-        for (size_t i = 0; i < vals.size(); ++i) ZKB_TRY(pool.fr(n, &polys[i]));
         if (vals.empty()) return ZKB_OK;
-        return ntt_many(vals, polys, pk->omega_inv, &pk->n_inv, nullptr);
+        Fr *pslab = nullptr;
+        ZKB_TRY(pool.fr(vals.size() * n, &pslab));
+        for (size_t i = 0; i < vals.size(); ++i) polys[i] = pslab + i * n;
+        const bool dealt = units_dealt(ctx, vals.size());   // multi-GPU: column i -> rank i mod P, gathered by one all-reduce
+        if (dealt) ZKB_CUDA(cudaMemsetAsync(pslab, 0, vals.size() * n * sizeof(Fr), st));
+        std::vector<Fr *> src, dst;
+        for (size_t i = 0; i < vals.size(); ++i)
+            if (unit_owned(ctx, i, vals.size())) { src.push_back(vals[i]); dst.push_back(polys[i]); }
+        if (!src.empty()) ZKB_TRY(ntt_many(src, dst, pk->omega_inv, &pk->n_inv, nullptr));
+        if (dealt) ZKB_TRY(comm_allreduce_u64(ctx, pslab, vals.size() * n * 4, st));
+        return ZKB_OK;
     };
     std::vector<Fr *> adv_polys, z_polys, phi_polys, m_polys;
     ZKB_TRY(to_coeff_new(s->adv_values, adv_polys));
