@@ -73,3 +73,25 @@ def test_csf_roundtrip_and_validation():
             Z.validate_csf(bad)
     with pytest.raises(zkb200.ZkbError):
         Z.validate_csf(blob[:20])
+
+
+def test_params_file_roundtrip(tmp_path, oracle):
+    """ParamsKZG file layout of the reference loader (prover/src/utils.rs:56-75): 4 B k | g | g_lagrange | g2 | s_g2, RawBytes."""
+    import numpy as np
+    import halo2_ref as H
+    from zkb200.params import ParamsKZG
+    k = 4
+    ref = H.Ref(H.ConstraintSystem(k, 0, 1, 0).finalize(), 777)
+    p = ParamsKZG(k, ref.g.copy(), ref.g_lagrange.copy(), bytes(range(128)), bytes(range(128, 256)))
+    path = tmp_path / "params4"
+    p.write_custom(str(path))
+    assert path.stat().st_size == ParamsKZG.expected_file_len(k) == 4 + 2 * 16 * 64 + 2 * 128
+    q = ParamsKZG.read_custom(str(path), to_device=False)
+    assert q.k == k and (q.g == ref.g).all() and (q.g_lagrange == ref.g_lagrange).all()
+    assert q.g2 == bytes(range(128)) and q.s_g2 == bytes(range(128, 256))
+    # every stored point is a valid raw G1Affine (Montgomery x || y on the curve)
+    assert all(oracle.g1_is_on_curve(pt) for pt in q.g)
+    with open(path, "ab") as f:
+        f.write(b"x")
+    with pytest.raises(ValueError):
+        ParamsKZG.read_custom(str(path), to_device=False)

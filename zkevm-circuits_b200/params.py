@@ -43,9 +43,47 @@ def g1_generator():
 
 
 class ParamsKZG:
-    def __init__(self, k, g, g_lagrange):
+    def __init__(self, k, g, g_lagrange, g2=None, s_g2=None):
         self.k, self.n = k, 1 << k
-        self.g, self.g_lagrange = g, g_lagrange          # device tensors (n, 8)
+        self.g, self.g_lagrange = g, g_lagrange          # (n, 8) device tensors (or host numpy arrays when read without a GPU)
+        self.g2, self.s_g2 = g2, s_g2                    # opaque 128-byte raw G2 points (only the verifier uses them)
+
+    # ---- params file I/O: ParamsKZG::read_custom / write_custom with SerdeFormat::RawBytes[Unchecked] --------------------
+    # Layout checked by the reference loader prover/src/utils.rs:56-75: 4 B k (LE u32) | g: 2^k x 64 B | g_lagrange: 2^k x 64 B |
+    # g2: 128 B | s_g2: 128 B, i.e. 4 + 2 * 2^k * 64 + 2 * 128 bytes; a raw G1 point is x || y as 4 x u64 LE Montgomery limbs
+    # each -- byte for byte the in-memory G1Affine the kernels consume, so loading is a copy.
+    @staticmethod
+    def expected_file_len(k):
+        return 4 + 2 * (1 << k) * 64 + 2 * 128
+
+    @staticmethod
+    def read_custom(path, to_device=True):
+        import os
+        with open(path, "rb") as f:
+            raw = f.read()
+        k = int.from_bytes(raw[:4], "little")
+        if len(raw) != ParamsKZG.expected_file_len(k):
+            raise ValueError(f"invalid params file len {len(raw)} for degree {k}")
+        n = 1 << k
+        g = np.frombuffer(raw, dtype=np.uint64, count=n * 8, offset=4).reshape(n, 8).copy()
+        gl = np.frombuffer(raw, dtype=np.uint64, count=n * 8, offset=4 + n * 64).reshape(n, 8).copy()
+        g2 = raw[4 + 2 * n * 64: 4 + 2 * n * 64 + 128]
+        s_g2 = raw[4 + 2 * n * 64 + 128:]
+        if to_device:
+            import torch
+            g = torch.from_numpy(g.view(np.int64)).cuda()
+            gl = torch.from_numpy(gl.view(np.int64)).cuda()
+        return ParamsKZG(k, g, gl, g2, s_g2)
+
+    def write_custom(self, path):
+        def host(a):
+            return a if isinstance(a, np.ndarray) else a.cpu().numpy().view(np.uint64)
+        with open(path, "wb") as f:
+            f.write(int(self.k).to_bytes(4, "little"))
+            f.write(np.ascontiguousarray(host(self.g)).tobytes())
+            f.write(np.ascontiguousarray(host(self.g_lagrange)).tobytes())
+            f.write(self.g2 if self.g2 is not None else bytes(128))
+            f.write(self.s_g2 if self.s_g2 is not None else bytes(128))
 
     @staticmethod
     def unsafe_setup_with_s(k, s):
