@@ -46,6 +46,12 @@ struct NttPlan {
     Fr *tw_lo = nullptr;   // omega^i,           i < 2^min(log_n, 12)
     Fr *tw_hi = nullptr;   // omega^(i * 2^12),  i < 2^(log_n - 12)   (log_n > 12)
     Fr *loc[3] = {nullptr, nullptr, nullptr};  // per pass: (omega_{2^a})^i, i < 2^(a-1)
+    // two-pass plans up to 2^25: the complete inter-pass twiddle table T[j_in * A + k] = omega^(j_in k) (x scale), n entries,
+    // so the boundary costs ONE multiply per element instead of two (lo x hi combine + apply)
+    Fr *tw_full = nullptr;
+    Fr *tw_full_scaled = nullptr;
+    Fr scaled_key;
+    bool has_scaled = false;
 };
 
 struct DeviceBuffer {

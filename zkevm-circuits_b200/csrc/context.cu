@@ -110,6 +110,8 @@ extern "C" int32_t zkb_destroy(zkb_ctx *ctx) {
         NttPlan &p = kv.second;
         if (p.tw_lo) cudaFree(p.tw_lo);
         if (p.tw_hi) cudaFree(p.tw_hi);
+        if (p.tw_full) cudaFree(p.tw_full);
+        if (p.tw_full_scaled) cudaFree(p.tw_full_scaled);
         for (int i = 0; i < 3; ++i)
             if (p.loc[i]) cudaFree(p.loc[i]);
     }

@@ -40,6 +40,7 @@ struct PassArgs {
     const Fr *scale;
     const Fr *in_scale;  // optional per-element input multiplier (first pass only): coset scaling tables
     // batching over blockIdx.y: column y reads in_tbl[y] (or in + y * in_stride) and writes out_tbl[y] (or out + y * out_stride)
+    const Fr *tw_full;   // optional complete inter-pass table (first pass of a two-pass plan)
     const Fr *const *in_tbl;
     Fr *const *out_tbl;
     uint64_t in_stride, out_stride;
@@ -178,22 +179,36 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const Fr *__restrict__ in
                 const uint32_t q = q0 + u * nt;
                 k[u] = __brev(q) >> (32 - p.a);
                 if (q < A) {
-                    const uint64_t e = (j_in * (uint64_t)k[u]) << p.tw_shift;
-                    tl[u] = fp_load(p.tw_lo + (e & ((1u << TW_LO_BITS) - 1)));
-                    if (two_level) th[u] = fp_load(p.tw_hi + (e >> TW_LO_BITS));
+                    if (p.tw_full) tl[u] = fp_load_stream(p.tw_full + (j_in << p.a) + k[u]);
+                    else {
+                        const uint64_t e = (j_in * (uint64_t)k[u]) << p.tw_shift;
+                        tl[u] = fp_load(p.tw_lo + (e & ((1u << TW_LO_BITS) - 1)));
+                        if (two_level) th[u] = fp_load(p.tw_hi + (e >> TW_LO_BITS));
+                    }
                 }
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const uint32_t q = q0 + u * nt;
                 if (q < A) {
-                    Fr tw = two_level ? fp_mul(tl[u], th[u]) : tl[u];
+                    Fr tw = (two_level && !p.tw_full) ? fp_mul(tl[u], th[u]) : tl[u];
                     const Fr v = fp_mul(smem_ld(lo, hi, q), tw);
                     fp_store_stream(out + base + ((uint64_t)k[u] << p.log_inner), v);
                 }
             }
         }
     }
+}
+
+// T[j_in * A + k] = lo[e & 4095] * hi[e >> 12], e = j_in * k  (lo may carry a folded scale)
+__global__ void build_full_table_kernel(const Fr *__restrict__ lo, const Fr *__restrict__ hi, uint32_t log_n, uint32_t a0, Fr *__restrict__ out) {
+    const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (idx >= (1ull << log_n)) return;
+    const uint64_t j_in = idx >> a0, k = idx & ((1ull << a0) - 1);
+    const uint64_t e = j_in * k;
+    Fr tw = fp_load(lo + (e & ((1u << TW_LO_BITS) - 1)));
+    if (log_n > TW_LO_BITS) tw = fp_mul(tw, fp_load(hi + (e >> TW_LO_BITS)));
+    fp_store(out + idx, tw);
 }
 
 __global__ void scale_table_kernel(const Fr *__restrict__ in, Fr *__restrict__ out, const Fr *__restrict__ scale, uint32_t n) {
@@ -315,6 +330,29 @@ int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, const Fr
         }
     }
 
+    // complete inter-pass table for two-pass plans (built once per plan / scale, n multiplies)
+    const Fr *tw_full = nullptr;
+    if (plan->npass == 2 && log_n <= 25) {
+        const unsigned bb = (unsigned)((n + 255) / 256);
+        if (!scale_host) {
+            if (!plan->tw_full) {
+                ZKB_CUDA(cudaMalloc((void **)&plan->tw_full, n * sizeof(Fr)));
+                build_full_table_kernel<<<bb, 256, 0, st>>>(plan->tw_lo, plan->tw_hi, log_n, plan->bits[0], plan->tw_full);
+                ctx->launches++;
+            }
+            tw_full = plan->tw_full;
+        } else {
+            if (!plan->tw_full_scaled) ZKB_CUDA(cudaMalloc((void **)&plan->tw_full_scaled, n * sizeof(Fr)));
+            if (!plan->has_scaled || !(plan->scaled_key == *scale_host)) {
+                build_full_table_kernel<<<bb, 256, 0, st>>>(tw_lo, plan->tw_hi, log_n, plan->bits[0], plan->tw_full_scaled);  // tw_lo = scaled copy
+                ctx->launches++;
+                plan->scaled_key = *scale_host;
+                plan->has_scaled = true;
+            }
+            tw_full = plan->tw_full_scaled;
+        }
+    }
+
     uint32_t log_inner = log_n;
     for (int ps = 0; ps < plan->npass; ++ps) {
         const uint32_t a = plan->bits[ps];
@@ -340,6 +378,7 @@ int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, const Fr
         p.tw_hi = plan->tw_hi;
         p.scale = d_scale;
         p.in_scale = (ps == 0) ? d_in_scale : nullptr;
+        p.tw_full = (ps == 0) ? tw_full : nullptr;
         p.in_tbl = nullptr;
         p.out_tbl = nullptr;
         p.in_stride = p.out_stride = 0;
