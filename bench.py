@@ -225,9 +225,11 @@ def main():
     achieved = (ALG_BYTES_PER_DIR / 2) / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                # dram__bytes_read.sum + dram__bytes_write.sum of one ntt_pass_kernel launch at 2^24 (ncu --set full capture
-                # profiles/r01_ntt_pass_v2_radix8_ncu.txt: 537.4 MB + 491.1 MB, average of the two passes); algorithmic 536.9 MB
-                "traffic": 1028.5e6,
+                # dram__bytes_read.sum + dram__bytes_write.sum per ntt_pass_kernel launch at 2^24, averaged over the two passes of a
+                # transform (ncu --set full, profiles/r01_ntt_pass_v3_final_ncu.txt): pass 1 = 1074 MB read (537 MB data + 537 MB
+                # complete inter-pass twiddle table: HBM traffic deliberately traded for one multiply per element) + 507 MB
+                # written, pass 2 = 537 MB + 489 MB.  Algorithmic: 536.9 MB per launch.
+                "traffic": 1303.9e6,
                 "note": "kernel is integer-multiply-pipe bound (1 Montgomery mul = 139 IMAD.WIDE per butterfly), see DESIGN.md; "
                         "alg bytes/launch = 2*32*2^24/2 passes"}
 
