@@ -7,8 +7,9 @@
 //
 // Device multiply: word-serial Montgomery (CIOS) on 32-bit limbs with two column-aligned accumulators
 // (even/odd) so that every 32x32->64 product is one mad.lo.cc/madc.hi.cc pair on adjacent limbs of a single
-// carry chain (ptxas fuses each pair into IMAD.WIDE with predicate carry).  264 IMADs per multiply; the kernel
-// class built on this is bound by the integer-multiply pipe (64 IMAD/clk/SM), not by HBM -- see DESIGN.md.
+// carry chain (ptxas fuses each pair into IMAD.WIDE with predicate carry): 122 IMAD.WIDE + 17 IMAD per multiply in SASS.
+// The kernel class built on this is bound by the integer-multiply pipe (fmaheavy: 64 32-bit products/clk/SM), not by HBM --
+// see DESIGN.md section 2.
 #pragma once
 #include <stdint.h>
 
