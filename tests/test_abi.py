@@ -95,3 +95,39 @@ def test_params_file_roundtrip(tmp_path, oracle):
         f.write(b"x")
     with pytest.raises(ValueError):
         ParamsKZG.read_custom(str(path), to_device=False)
+
+
+def test_proof_container_matches_fixture(golden, tmp_path):
+    """prover::Proof container (prover/src/proof.rs): the fixture's own chunk proof round-trips byte for byte, instances are
+    32-byte big-endian words."""
+    import base64
+    from zkb200.proof_io import Proof, serialize_instances
+    proof, inst, vk = bytes.fromhex(golden["proof_hex"]), bytes.fromhex(golden["instances_hex"]), bytes.fromhex(golden["vk_hex"])
+    p = Proof(proof, inst, vk, golden["git_version"])
+    vals = p.instances()
+    assert len(vals) == 1 and len(vals[0]) == golden["num_instance"][0] == 44
+    assert all(v < 21888242871839275222246405745257275088548364400416034343698204186575808495617 for v in vals[0])
+    # the 32 public-input bytes of the chunk sit in the last 32 instance cells, each < 256 (SURVEY appendix B)
+    assert all(v < 256 for v in vals[0][12:])
+    assert serialize_instances(vals) == inst
+    o = p.to_json_obj()
+    assert base64.b64decode(o["proof"]) == proof and base64.b64decode(o["instances"]) == inst and base64.b64decode(o["vk"]) == vk
+    p.dump(str(tmp_path), "chunk_0")
+    q = Proof.from_json_file(str(tmp_path), "chunk_0")
+    assert (q.proof, q.instances_raw, q.vk, q.git_version) == (proof, inst, vk, golden["git_version"])
+    assert (tmp_path / "vk_chunk_0.vkey").read_bytes() == vk
+
+
+def test_product_never_imports_the_oracle():
+    """The product path must not route through oracle/ (only tests, smoke() and bench.py's baseline legs may)."""
+    import re
+    bad = re.compile(r"^\s*(import|from)\s+(oracle_lib|pyref|halo2_ref|oracle)\b", re.M)
+    pkg = os.path.join(ROOT, "zkevm-circuits_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert not bad.search(src), fn
+                assert "libzkoracle" not in src and "zko_" not in src, fn
+    src = open(os.path.join(ROOT, "scripts", "proof_bench.py")).read()
+    assert not bad.search(src)
