@@ -172,7 +172,7 @@ class Domain:
 
 class Ref:
     """Reference prover/verifier bound to one (cs, srs)."""
-    def __init__(self, cs, srs_s):
+    def __init__(self, cs, srs_s, build_srs=True):
         self.F = FA()
         self.o = self.F.o
         self.cs = cs
@@ -180,8 +180,10 @@ class Ref:
         self.dom = Domain(cs.k, self.d)
         self.bf = cs.blinding_factors()
         self.chunk = self.d - 2
-        self.s = srs_s % R
+        self.s = (srs_s or 0) % R
         n = cs.n
+        if not build_srs:       # verify-only use (e.g. the reference's k = 25 fixture proof): no SRS needed
+            return
         # ParamsKZG::unsafe_setup_with_s: g[i] = [s^i] G ; g_lagrange[i] = [L_i(s)] G  (poly/kzg/commitment.rs)
         G = self.o.g1_generator()
         pw = self.o.fr_powers(self.F.arr([self.s])[0], n)
@@ -659,9 +661,11 @@ class Ref:
         if op == SCALED: return self.eval_expr_at(e.a, ev, challenges) * e.b % R
         raise ValueError
 
-    def verify_proof(self, pk, transcript_repr, instances, proof):
+    def verify_proof(self, pk, transcript_repr, instances, proof, reader=None, decide=None):
+        """reader: transcript reader (default Blake2b); decide(lhs, rhs): final KZG accumulator check e(lhs, g2) == e(rhs, s_g2)
+        (default: the known-s trapdoor check in G1)."""
         cs, dom, n, bf = self.cs, self.dom, self.cs.n, self.bf
-        rd = Ref.Reader(self, proof)
+        rd = reader or Ref.Reader(self, proof)
         rd.common_scalar(transcript_repr)
         for col in instances:
             for v in col: rd.common_scalar(v % R)
@@ -804,4 +808,6 @@ class Ref:
         right = P.g1_add(right, P.g1_mul(h1, (-z0) % R))
         right = P.g1_add(right, P.g1_mul(h2, u))
         # pairing check e(h2, [s]G2) == e(right, G2)  <=>  [s] h2 == right   (s known in tests)
+        if decide is not None:
+            return decide(right, h2)
         return P.g1_mul(h2, self.s) == right

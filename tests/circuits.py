@@ -146,10 +146,8 @@ class ThinCompressionShape:
       permutation over [fixed 1, advice 0, instance 0]         (one chunk: cs degree 5 -> chunk length 3)
     Expected proof layout (fixture): 1 advice + 1 m + z, phi, random + 4 h pieces + 17 evals + 2 = 28 items."""
 
-    def __init__(self, k, seed=0, n_instance=6):
-        rnd = random.Random(seed)
-        self.k, self.n = k, 1 << k
-        n = self.n
+    @staticmethod
+    def constraint_system(k):
         cs = H.ConstraintSystem(k, 4, 1, 1)
         a = lambda r=0: H.advice(0, r)
         cs.gates.append(H.fixed(2) * (a(0) + a(1) * a(2) - a(3)))
@@ -159,6 +157,13 @@ class ThinCompressionShape:
         # the fixture's evaluation order lists fixed column 1 (constants, from the permutation) before column 0: halo2 records
         # queries in configure() order (enable_equality on the constants column happens before the lookup table is queried)
         cs.fixed_queries = [(1, 0), (0, 0), (2, 0), (3, 0)]
+        return cs
+
+    def __init__(self, k, seed=0, n_instance=6):
+        rnd = random.Random(seed)
+        self.k, self.n = k, 1 << k
+        n = self.n
+        cs = self.constraint_system(k)
         self.cs = cs
         bf = cs.blinding_factors()
         assert bf == 6 and cs.degree() == 5
