@@ -174,6 +174,12 @@ ZKB_API int32_t zkb_pk_vk_bytes(zkb_pk *pk, uint8_t *out, uint64_t cap, uint64_t
 ZKB_API int32_t zkb_csf_validate(const uint32_t *csf, uint64_t csf_words);
 ZKB_API int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4], const uint64_t *const *instance_values,
                                 const uint32_t *instance_lens, zkb_session **out);
+/* Same with a choice of transcript: 0 = Blake2bWrite/Challenge255 (the reference's benches, circuit-benchmarks/src/super_circuit.rs:112),
+ * 1 = snark-verifier-sdk PoseidonTranscript<NativeLoader> (gen_snark_shplonk, prover/src/common/prover/utils.rs:31): Poseidon T=5,
+ * RATE=4, R_F=8, R_P=60 over Fr; points absorbed as (x mod r, y mod r).  The Poseidon restatement is pinned by the reference's own
+ * chunk proof (tests/test_fixture_proof.py).                                                                                    */
+ZKB_API int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const uint64_t transcript_repr[4],
+                                   const uint64_t *const *instance_values, const uint32_t *instance_lens, zkb_session **out);
 ZKB_API int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const uint64_t *const *advice_columns,
                                        uint64_t *challenges_out);
 ZKB_API int32_t zkb_prove_finish(zkb_session *s, const uint64_t *z_blinds, const uint64_t *phi_blinds,

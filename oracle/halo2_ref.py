@@ -314,8 +314,57 @@ class Ref:
             self.h.update(b"\x00")
             return int.from_bytes(self.h.copy().digest(), "little") % R
 
+    class PoseidonTranscript:
+        """Writer side of snark_verifier_sdk's PoseidonTranscript<NativeLoader> (gen_snark_shplonk: prover/src/common/prover/utils.rs:31):
+        points are absorbed as (x mod r, y mod r), proof bytes are the same compressed points / LE scalars.  The hash itself
+        (oracle/poseidon_ref.py) is pinned by tests/test_fixture_proof.py."""
+        def __init__(self, ref, spec=None):
+            import poseidon_ref as PO
+            self.h = PO.Poseidon(spec or PO.Spec(5, 8, 60))
+            self.buf = bytearray()
+            self.ref = ref
+
+        def common_scalar(self, v): self.h.update([int(v) % R])
+
+        def common_point(self, aff):
+            x = P.from_mont(P.from_limbs(aff[:4]), P.Q_MOD); y = P.from_mont(P.from_limbs(aff[4:]), P.Q_MOD)
+            assert not (x == 0 and y == 0), "cannot write points at infinity to the transcript"
+            self.h.update([x % R, y % R])
+
+        def write_point(self, aff):
+            self.common_point(aff)
+            self.buf += self.ref.o.g1_compress(aff)
+
+        def write_scalar(self, v):
+            self.common_scalar(v)
+            self.buf += int(v).to_bytes(32, "little")
+
+        def squeeze(self): return self.h.squeeze()
+
+    class PoseidonReader:
+        def __init__(self, proof, spec=None):
+            import poseidon_ref as PO
+            self.h, self.p, self.pos = PO.Poseidon(spec or PO.Spec(5, 8, 60)), proof, 0
+
+        def common_scalar(self, v): self.h.update([int(v) % R])
+
+        def read_point(self):
+            b = self.p[self.pos: self.pos + 32]; self.pos += 32
+            pt = P.g1_decompress(b)
+            assert pt is not None and P.g1_is_on_curve(pt)
+            self.h.update([pt[0] % R, pt[1] % R])
+            return pt
+
+        def read_scalar(self):
+            v = int.from_bytes(self.p[self.pos: self.pos + 32], "little"); self.pos += 32
+            assert v < R
+            self.h.update([v])
+            return v
+
+        def squeeze(self): return self.h.squeeze()
+
     # ---- create_proof (plonk/prover.rs)
-    def create_proof(self, pk, transcript_repr, instances, synthesize, blinds):
+    def create_proof(self, pk, transcript_repr, instances, synthesize, blinds, transcript=None):
         """instances: list (per instance column) of lists of ints.
         synthesize(phase, challenges) -> dict advice column index -> (n,4) array, already blinded in the last bf+1 rows
         (rows >= n - (bf + 1) random), for the columns of that phase.
@@ -323,7 +372,7 @@ class Ref:
         Returns (proof bytes, debug dict)."""
         F, cs, dom, n, bf = self.F, self.cs, self.dom, self.cs.n, self.bf
         dbg = {}
-        tr = Ref.Transcript(self)
+        tr = transcript or Ref.Transcript(self)
         tr.common_scalar(transcript_repr)
         inst_values = []
         for col in instances:

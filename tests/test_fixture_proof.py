@@ -17,28 +17,7 @@ from circuits import ThinCompressionShape
 R = P.R_MOD
 
 
-class PoseidonReader:
-    """snark_verifier PoseidonTranscript<NativeLoader>: points are absorbed as (x mod r, y mod r), scalars as is."""
-
-    def __init__(self, proof, spec):
-        self.h, self.p, self.pos = PO.Poseidon(spec), proof, 0
-
-    def common_scalar(self, v): self.h.update([v % R])
-
-    def read_point(self):
-        b = self.p[self.pos: self.pos + 32]; self.pos += 32
-        pt = P.g1_decompress(b)
-        assert pt is not None and P.g1_is_on_curve(pt)
-        self.h.update([pt[0] % R, pt[1] % R])
-        return pt
-
-    def read_scalar(self):
-        v = int.from_bytes(self.p[self.pos: self.pos + 32], "little"); self.pos += 32
-        assert v < R
-        self.h.update([v])
-        return v
-
-    def squeeze(self): return self.h.squeeze()
+PoseidonReader = H.Ref.PoseidonReader     # snark_verifier PoseidonTranscript<NativeLoader>: points absorbed as (x mod r, y mod r)
 
 
 @pytest.fixture(scope="module")

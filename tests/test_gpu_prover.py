@@ -106,3 +106,25 @@ def test_vk_bytes_processed_format():
     assert len(vk) == 8 + 32 * len(pts)
     for i, aff in enumerate(pts):
         assert vk[8 + 32 * i: 40 + 32 * i] == ref.o.g1_compress(aff)
+
+
+@pytest.mark.parametrize("kind,k", [("toy", 6), ("thin", 8)])
+def test_create_proof_poseidon_transcript_matches_oracle(kind, k):
+    """gen_snark_shplonk's transcript: the CUDA session with the Poseidon transcript == the oracle's Poseidon prover byte for byte,
+    and the fixture-pinned verifier (Poseidon reader) accepts it."""
+    from zkb200 import plonk as Z
+    tc = (ToyCircuit if kind == "toy" else ThinCompressionShape)(k, seed=200 + k)
+    ref = H.Ref(tc.cs, 1234)
+    F = ref.F
+    fixed = [F.arr(c) for c in tc.fixed_ints]
+    pkr = ref.keygen(fixed, tc.copies)
+    rp = F.arr(tc.blinds_ints["random_poly"])
+    blinds = {"z": tc.blinds_ints["z"], "phi": tc.blinds_ints["phi"], "random_poly": rp}
+    synth_ref = lambda phase, ch: {c: F.arr(v) for c, v in tc.advice_ints(phase, ch).items()}
+    proof_ref, _ = ref.create_proof(pkr, tc.transcript_repr, tc.instances, synth_ref, blinds, transcript=H.Ref.PoseidonTranscript(ref))
+    pk = Z.ProvingKey(to_product_cs(tc.cs, ref.bf, ref.d), fixed, pkr["sigma_values"], ref.g, ref.g_lagrange)
+    synth = lambda phase, ch: {c: F.arr(v) for c, v in tc.advice_ints(phase, {i: F.ints(v[None])[0] for i, v in ch.items()}).items()}
+    zb = np.concatenate([F.arr(b) for b in tc.blinds_ints["z"]]); pb = np.concatenate([F.arr(b) for b in tc.blinds_ints["phi"]])
+    proof = Z.create_proof(pk, F.arr([tc.transcript_repr])[0], [F.arr(c) for c in tc.instances], synth, zb, pb, rp, transcript="poseidon")
+    assert first_diff(proof, proof_ref) is None, f"first differing 32-byte proof item: {first_diff(proof, proof_ref)}"
+    assert ref.verify_proof(pkr, tc.transcript_repr, tc.instances, proof, reader=H.Ref.PoseidonReader(proof))

@@ -83,3 +83,20 @@ def test_gates_only_circuit():
     tc = GatesOnlyCircuit(5, seed=9)
     ref, pk, proof, _ = prove(tc)
     assert ref.verify_proof(pk, tc.transcript_repr, tc.instances, proof)
+
+
+@pytest.mark.parametrize("kind,k", [("toy", 5), ("thin", 6)])
+def test_prove_verify_with_poseidon_transcript(kind, k):
+    """create_proof with the SDK's Poseidon transcript (what gen_snark_shplonk uses); the Poseidon restatement and the verifier are
+    pinned by the reference's own proof in tests/test_fixture_proof.py."""
+    tc = (ToyCircuit if kind == "toy" else ThinCompressionShape)(k, seed=70 + k)
+    ref = H.Ref(tc.cs, 1234)
+    F = ref.F
+    pk = ref.keygen([F.arr(c) for c in tc.fixed_ints], tc.copies)
+    blinds = {"z": tc.blinds_ints["z"], "phi": tc.blinds_ints["phi"], "random_poly": F.arr(tc.blinds_ints["random_poly"])}
+    synth = lambda phase, ch: {c: F.arr(v) for c, v in tc.advice_ints(phase, ch).items()}
+    proof, _ = ref.create_proof(pk, tc.transcript_repr, tc.instances, synth, blinds, transcript=H.Ref.PoseidonTranscript(ref))
+    assert ref.verify_proof(pk, tc.transcript_repr, tc.instances, proof, reader=H.Ref.PoseidonReader(proof))
+    assert not ref.verify_proof(pk, tc.transcript_repr, tc.instances, proof)          # a Blake2b reader must not accept it
+    proof_b, _ = ref.create_proof(pk, tc.transcript_repr, tc.instances, synth, blinds)
+    assert proof_b != proof and len(proof_b) == len(proof)

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "expr.cuh"
 #include "blake2b.h"
+#include "poseidon.h"
 #include <algorithm>
 #include <memory>
 #include <string.h>
@@ -204,7 +205,9 @@ struct zkb_pk {
 
 struct zkb_session {
     zkb_pk *pk = nullptr;
+    int tkind = 0;  // 0: Blake2bWrite<_, G1Affine, Challenge255<_>> (benches), 1: snark-verifier-sdk PoseidonTranscript (gen_snark_shplonk)
     Blake2b tr{"Halo2-Transcript"};
+    PoseidonSponge pos;
     std::vector<uint8_t> proof;
     DevPool pool;
     std::vector<Fr *> inst_values, inst_polys, adv_values;
@@ -216,7 +219,24 @@ struct zkb_session {
 namespace zkb {
 
 // ---------------------------------------------------------------------------------------------------------- transcript
+// base-field coordinate (canonical limbs, < q) -> scalar-field element (x mod r), Montgomery form: snark-verifier's fe_to_fe
+static Fr fq_canonical_to_fr(const Fq &c) {
+    uint32_t v[8];
+    for (int i = 0; i < 8; ++i) v[i] = c.l[i];
+    bool ge = true;
+    for (int i = 7; i >= 0; --i) {
+        if (v[i] != FrParams::P(i)) { ge = v[i] > FrParams::P(i); break; }
+    }
+    if (ge) {  // q < 2r: one subtraction suffices
+        int64_t br = 0;
+        for (int i = 0; i < 8; ++i) { int64_t d = (int64_t)v[i] - FrParams::P(i) + br; v[i] = (uint32_t)d; br = d >> 32; }
+    }
+    Fr out;
+    for (int i = 0; i < 8; ++i) out.l[i] = v[i];
+    return fp_from_canonical(out);
+}
 static void tr_common_scalar(zkb_session *s, const Fr &v) {
+    if (s->tkind == 1) { s->pos.update(v); return; }
     const uint8_t pre = 2;
     Fr c = fp_to_canonical(v);
     s->tr.update(&pre, 1);
@@ -230,17 +250,23 @@ static void tr_write_scalar(zkb_session *s, const Fr &v) {
 }
 static int32_t tr_write_point(zkb_session *s, const G1Affine &p) {
     if (p.is_identity()) { set_error("cannot write points at infinity to the transcript"); return ZKB_ERR_STATE; }
-    const uint8_t pre = 1;
     Fq x = fp_to_canonical(p.x), y = fp_to_canonical(p.y);
-    s->tr.update(&pre, 1);
-    s->tr.update(x.l, 32);
-    s->tr.update(y.l, 32);
+    if (s->tkind == 1) {
+        s->pos.update(fq_canonical_to_fr(x));
+        s->pos.update(fq_canonical_to_fr(y));
+    } else {
+        const uint8_t pre = 1;
+        s->tr.update(&pre, 1);
+        s->tr.update(x.l, 32);
+        s->tr.update(y.l, 32);
+    }
     uint8_t comp[32];
     g1_compress(p, comp);
     s->proof.insert(s->proof.end(), comp, comp + 32);
     return ZKB_OK;
 }
 static Fr tr_squeeze(zkb_session *s) {
+    if (s->tkind == 1) return s->pos.squeeze();
     const uint8_t pre = 0;
     s->tr.update(&pre, 1);
     uint8_t h[64];
@@ -548,12 +574,20 @@ extern "C" int32_t zkb_pk_destroy(zkb_pk *pk) {
 }
 
 // ================================================================================================ C ABI: proof session
+extern "C" int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const uint64_t transcript_repr[4], const uint64_t *const *instance_values,
+                                      const uint32_t *instance_lens, zkb_session **out);
 extern "C" int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4], const uint64_t *const *instance_values, const uint32_t *instance_lens,
                                    zkb_session **out) {
+    return zkb_prove_begin_ex(pk, 0, transcript_repr, instance_values, instance_lens, out);
+}
+extern "C" int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const uint64_t transcript_repr[4], const uint64_t *const *instance_values,
+                                      const uint32_t *instance_lens, zkb_session **out) {
     ZKB_ARG(pk && transcript_repr && out && (pk->cs.ni == 0 || (instance_values && instance_lens)));
+    ZKB_ARG(transcript_kind == 0 || transcript_kind == 1);
     ZKB_CUDA(cudaSetDevice(pk->ctx->device));
     std::unique_ptr<zkb_session> s(new zkb_session());
     s->pk = pk;
+    s->tkind = transcript_kind;
     s->pool.ctx = pk->ctx;
     const Csf &cs = pk->cs;
     const uint64_t n = pk->n;

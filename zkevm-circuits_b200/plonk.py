@@ -149,8 +149,12 @@ class ProvingKey:
         except Exception: pass
 
 
-def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blinds, random_poly):
-    """Mirror of plonk::create_proof for one circuit with a Blake2b transcript.
+TRANSCRIPTS = {"blake2b": 0, "poseidon": 1}
+
+
+def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blinds, random_poly, transcript="blake2b"):
+    """Mirror of plonk::create_proof for one circuit; transcript = "blake2b" (Blake2bWrite, the reference's benches) or "poseidon"
+    (snark-verifier-sdk's PoseidonTranscript, what gen_snark_shplonk uses).
 
     transcript_repr: uint64[4] (Montgomery Fr).   instances: list of uint64 (len, 4) arrays (one per instance column).
     synthesize(phase, challenges) -> dict {advice column: uint64 (n,4) array, already blinded} for that phase's columns,
@@ -162,7 +166,7 @@ def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blind
     ki, itbl = _ptr_array(instances)
     lens = (ctypes.c_uint32 * max(1, len(instances)))(*[a.shape[0] for a in instances])
     sess = _vp()
-    check(lib.zkb_prove_begin(pk.handle, _vp(tr.ctypes.data), ctypes.cast(itbl, _vp), ctypes.cast(lens, _vp), ctypes.byref(sess)))
+    check(lib.zkb_prove_begin_ex(pk.handle, TRANSCRIPTS[transcript], _vp(tr.ctypes.data), ctypes.cast(itbl, _vp), ctypes.cast(lens, _vp), ctypes.byref(sess)))
     try:
         nch = len(cs.challenge_phase)
         ch_buf = np.zeros((max(1, nch), 4), dtype=np.uint64)
