@@ -270,6 +270,19 @@ def main():
         except Exception as e:  # keep the headline line even if the extra fails
             extras["proof_error"] = repr(e)
     barrier()
+    if not args.no_proof and world > 1:
+        # one proof spread over all ranks (commitment batches, coset parts, lookups dealt across the GPUs over NCCL): strong scaling of
+        # BASELINE configs[3] (SuperCircuit-shaped k = 20); every rank participates, rank 0 reports
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import multi_gpu_proof
+        try:
+            res = multi_gpu_proof.run(20, 64, 8, 16, reps=2)
+            if rank == 0:
+                extras["proof_super_shape_k20_multi_gpu"] = res
+        except Exception as e:
+            if rank == 0:
+                extras["proof_multi_gpu_error"] = repr(e)
+    barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -7,11 +7,9 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
 
 
-def main():
-    k, ng, nl, npm = [int(x) for x in sys.argv[1:5]]
+def run(k, ng, nl, npm, reps=3):
+    """all ranks of an initialised NCCL process group call this; returns the result dict on rank 0 (None elsewhere)."""
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import zkb200
     from zkb200 import plonk as Z
     from zkb200.synth import WideCircuit
@@ -31,7 +29,7 @@ def main():
         return cols0 if phase == 0 else {c: h(t) for c, t in wc.synthesize_dev(phase, ch).items()}
     zb, pb, rp, tr = h(wc.z_blinds), h(wc.phi_blinds), h(wc.random_poly), h(wc.transcript_repr[None])[0]
 
-    def timed(pk, reps=3):
+    def timed(pk):
         best, proof = 1e9, None
         for _ in range(reps):
             dist.barrier(); torch.cuda.synchronize()
@@ -50,10 +48,23 @@ def main():
     pkn = Z.ProvingKey(wc.cs, fixed, sigma, g, gl, ctx=ctxn)
     proofn, tn = timed(pkn)
     same = torch.tensor([int(proofn == proof1)], device="cuda"); dist.all_reduce(same, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print(json.dumps({"k": k, "world": world, "advice_columns": wc.cs.num_advice, "single_gpu_seconds": t1, "multi_gpu_seconds": tn,
-                          "speedup": t1 / tn, "identical_proof_on_all_ranks": bool(same.item()), "proof_sha256": hashlib.sha256(proofn).hexdigest()[:16]}))
     pkn.close()
+    ctxn.close()
+    ctx1.close()
+    if rank == 0:
+        return {"k": k, "world": world, "advice_columns": wc.cs.num_advice, "single_gpu_seconds": t1, "multi_gpu_seconds": tn,
+                "speedup": t1 / tn, "identical_proof_on_all_ranks": bool(same.item()), "proof_sha256": hashlib.sha256(proofn).hexdigest()[:16]}
+    return None
+
+
+def main():
+    k, ng, nl, npm = [int(x) for x in sys.argv[1:5]]
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = run(k, ng, nl, npm)
+    if res is not None:
+        print(json.dumps(res))
     dist.destroy_process_group()
 
 
