@@ -26,6 +26,8 @@ ALG_BYTES_PER_DIR = 2 * 32 * N_PTS                  # 1,073,741,824 B: read + wr
 METRIC = "NTT Fr-butterflies/s (2^24 fwd+inv round trip)"
 UNIT = "butterflies/s"
 MSM_LOG_N = 20
+CONFIG = {"workload": "2^24-point Fr NTT forward+inverse round trip per GPU (BASELINE configs[1])", "log_n": LOG_N,
+          "l2": "working set 512 MiB per transform > 126 MB L2 (no flush needed)", "per_rank": "independent transform per rank"}
 
 
 def dist_env():
@@ -112,7 +114,7 @@ def run_reference(args):
     cores = orc.num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery, BN254 Fr)",
-            "data": "synthetic", "config": {"workload": "2^24-point Fr NTT forward+inverse round trip (BASELINE configs[1])", "log_n": LOG_N},
+            "data": "synthetic", "config": CONFIG,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps} full 2^24 fwd+inv round trips, oracle best_fft (OpenMP)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -302,8 +304,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u256 (8x u32 Montgomery limbs, BN254 Fr)", "data": "synthetic",
-                "config": {"workload": "2^24-point Fr NTT forward+inverse round trip per GPU (BASELINE configs[1])", "log_n": LOG_N,
-                           "l2": "working set 512 MiB per transform > 126 MB L2 (no flush needed)", "per_rank": "independent transform per rank"},
+                "config": CONFIG,
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * 32 * N_PTS, "d2h_bytes_per_step": 2 * 32 * N_PTS},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "extras": extras}
         print(json.dumps(line), flush=True)
