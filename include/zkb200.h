@@ -180,6 +180,11 @@ ZKB_API int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4], c
  * chunk proof (tests/test_fixture_proof.py).                                                                                    */
 ZKB_API int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const uint64_t transcript_repr[4],
                                    const uint64_t *const *instance_values, const uint32_t *instance_lens, zkb_session **out);
+/* Host-only transcript primitives (no CUDA device needed; used by the CPU test-suite to pin the session's hashers):
+ * zkb_poseidon_hash_host        absorb n Fr (Montgomery) into a fresh PoseidonTranscript sponge, squeeze one challenge
+ * zkb_blake2b_challenge_host    feed bytes to a fresh Blake2b("Halo2-Transcript") state, squeeze one Challenge255 (mod r)          */
+ZKB_API int32_t zkb_poseidon_hash_host(const uint64_t *inputs, uint64_t n, uint64_t out[4]);
+ZKB_API int32_t zkb_blake2b_challenge_host(const uint8_t *bytes, uint64_t len, uint64_t out[4]);
 ZKB_API int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const uint64_t *const *advice_columns,
                                        uint64_t *challenges_out);
 ZKB_API int32_t zkb_prove_finish(zkb_session *s, const uint64_t *z_blinds, const uint64_t *phi_blinds,

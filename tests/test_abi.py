@@ -131,3 +131,32 @@ def test_product_never_imports_the_oracle():
                 assert "libzkoracle" not in src and "zko_" not in src, fn
     src = open(os.path.join(ROOT, "scripts", "proof_bench.py")).read()
     assert not bad.search(src)
+
+
+def test_session_hashers_host_side(oracle):
+    """The two transcripts of the proving session, pinned on the CPU: Poseidon vs the fixture-pinned restatement
+    (oracle/poseidon_ref.py), Blake2b challenge vs hashlib."""
+    import ctypes, hashlib, random
+    import numpy as np
+    import zkb200
+    import pyref as P
+    import poseidon_ref as PO
+    lib = zkb200.load_library()
+    rnd = random.Random(9)
+    spec = PO.Spec(5, 8, 60)
+    for n in (0, 1, 3, 4, 5, 8, 13):
+        vals = [rnd.randrange(P.R_MOD) for _ in range(n)]
+        a = np.array([P.limbs(P.to_mont(v, P.R_MOD)) for v in vals], dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros(4, dtype=np.uint64)
+        assert lib.zkb_poseidon_hash_host(ctypes.c_void_p(a.ctypes.data) if n else None, n, ctypes.c_void_p(out.ctypes.data)) == 0
+        sp = PO.Poseidon(spec)
+        sp.update(vals)
+        assert P.from_mont(P.from_limbs(out), P.R_MOD) == sp.squeeze()
+    for ln in (0, 1, 32, 127, 128, 129, 300):
+        data = bytes(rnd.randrange(256) for _ in range(ln))
+        out = np.zeros(4, dtype=np.uint64)
+        buf = (ctypes.c_uint8 * max(1, ln)).from_buffer_copy(data or b"\0")
+        assert lib.zkb_blake2b_challenge_host(ctypes.cast(buf, ctypes.c_void_p) if ln else None, ln, ctypes.c_void_p(out.ctypes.data)) == 0
+        h = hashlib.blake2b(digest_size=64, person=b"Halo2-Transcript")
+        h.update(data + b"\x00")
+        assert P.from_mont(P.from_limbs(out), P.R_MOD) == int.from_bytes(h.digest(), "little") % P.R_MOD

@@ -503,6 +503,38 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
     return ZKB_OK;
 }
 
+// ---- host-only transcript primitives (no device needed): let the CPU test-suite pin the two hashers of the proving session ----
+// absorb n Fr elements (Montgomery) into a fresh Poseidon sponge (PoseidonTranscript::common_scalar) and squeeze one challenge
+extern "C" int32_t zkb_poseidon_hash_host(const uint64_t *inputs, uint64_t n, uint64_t out[4]) {
+    ZKB_ARG(out && (inputs || n == 0));
+    PoseidonSponge sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        Fr v;
+        memcpy(v.l, inputs + 4 * i, 32);
+        sp.update(v);
+    }
+    const Fr c = sp.squeeze();
+    memcpy(out, c.l, 32);
+    return ZKB_OK;
+}
+// feed raw bytes to a fresh Blake2b("Halo2-Transcript") state and squeeze one Challenge255 (prefix 0x00, 64-byte digest mod r)
+extern "C" int32_t zkb_blake2b_challenge_host(const uint8_t *bytes, uint64_t len, uint64_t out[4]) {
+    ZKB_ARG(out && (bytes || len == 0));
+    Blake2b st("Halo2-Transcript");
+    if (len) st.update(bytes, len);
+    const uint8_t pre = 0;
+    st.update(&pre, 1);
+    uint8_t h[64];
+    st.finalize_copy(h);
+    Fr lo, hi;
+    memcpy(lo.l, h, 32);
+    memcpy(hi.l, h + 32, 32);
+    const Fr r2 = Fr::r2();
+    const Fr c = fp_add(fp_mul(lo, r2), fp_mul(fp_mul(hi, r2), r2));
+    memcpy(out, c.l, 32);
+    return ZKB_OK;
+}
+
 // VerifyingKey::write(SerdeFormat::Processed) (halo2_proofs plonk.rs): u32 BE k || u32 BE num_fixed || fixed commitments ||
 // permutation commitments, points compressed -- the layout of the reference fixture's `vk` (aggregator/data/batch-task.json:
 // 0x19, 4, 4 + 3 points = 232 B).  Commitments = commit_lagrange of the fixed / sigma columns (keygen.rs), batched MSMs.
