@@ -710,7 +710,7 @@ class Ref:
         if op == SCALED: return self.eval_expr_at(e.a, ev, challenges) * e.b % R
         raise ValueError
 
-    def verify_proof(self, pk, transcript_repr, instances, proof, reader=None, decide=None):
+    def verify_proof(self, pk, transcript_repr, instances, proof, reader=None, decide=None, dbg=None):
         """reader: transcript reader (default Blake2b); decide(lhs, rhs): final KZG accumulator check e(lhs, g2) == e(rhs, s_g2)
         (default: the known-s trapdoor check in G1)."""
         cs, dom, n, bf = self.cs, self.dom, self.cs.n, self.bf
@@ -807,6 +807,10 @@ class Ref:
             rhs = (tb * ssum - m_x * prod) % R
             fold(l0 * phi_x % R); fold(llast * phi_x % R); fold(lactive * (lhs - rhs) % R)
         expected_h = acc * pow(xn - 1, -1, R) % R
+        if dbg is not None:
+            dbg.update(dict(numerator=acc, x=x, y=y, theta=theta, beta=beta, gamma=gamma, challenges=dict(challenges), evals=dict(ev),
+                            l0=l0, l_last=llast, l_blind=lblind, sigma_evals=list(sig_ev), z_evals=list(z_ev), lookup_evals=list(lk_ev),
+                            random_eval=rand_eval))
         # h commitment = sum x^(n i) H_i
         hc = None
         for c in reversed(h_c): hc = P.g1_add(P.g1_mul(hc, xn) if hc else None, c)

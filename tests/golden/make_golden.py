@@ -32,6 +32,9 @@ def main():
         "queries": pr["queries"],
         "quotient_num_chunk": pr["quotient"]["num_chunk"],
         "transcript_initial_state": pr["transcript_initial_state"],
+        # snark-verifier's own spelling of the quotient numerator (expression tree over polys p0..p12, challenges, Lagrange
+        # polynomials): tests/test_fixture_proof.py evaluates it at the proof's point and compares with the oracle's formulas
+        "quotient_numerator": pr["quotient"]["numerator"],
     }
     # Montgomery-form constants appearing inside the quotient numerator: 1, DELTA, DELTA^2
     consts = []

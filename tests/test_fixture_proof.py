@@ -62,3 +62,52 @@ def test_reference_fixture_rejects_tampering(setup):
     assert not ref.verify_proof(pk, (tis + 1) % R, instances, proof, reader=PoseidonReader(proof, spec), decide=decide)
     # wrong Poseidon parameters break the Fiat-Shamir challenges
     assert not ref.verify_proof(pk, tis, instances, proof, reader=PoseidonReader(proof, PO.Spec(5, 8, 57)), decide=decide)
+
+
+def test_numerator_formulas_match_snark_verifier_expression(setup, golden):
+    """Row a4's constraint formulas, term by term: evaluate snark-verifier's OWN expression tree for the quotient numerator (stored
+    in the fixture's Protocol) at the proof's evaluation point and challenges, and compare with the numerator the oracle computes
+    from its restated halo2 formulas (custom gate, permutation argument, mv-lookup/logUp, y-Horner order)."""
+    ref, pk, tis, instances, proof, spec, decide = setup
+    dbg = {}
+    assert ref.verify_proof(pk, tis, instances, proof, reader=PoseidonReader(proof, spec), decide=decide, dbg=dbg)
+    n, x = ref.cs.n, dbg["x"]
+    xn = pow(x, n, R)
+    omega = ref.dom.omega
+    chal = [dbg["theta"], dbg["beta"], dbg["gamma"], dbg["y"]]                 # ch0..ch3 of the Protocol
+    ev = dbg["evals"]
+    # snark-verifier polynomial numbering: p0-p3 fixed, p4-p6 sigma, p7 instance, p8 advice, p9 m, p10 z, p11 phi, p12 random
+    poly_eval = {}
+    for c in range(4): poly_eval[(c, 0)] = ev[(H.FIXED, c, 0)]
+    for i, v in enumerate(dbg["sigma_evals"]): poly_eval[(4 + i, 0)] = v
+    poly_eval[(7, 0)] = ev[(H.INSTANCE, 0, 0)]
+    for r in range(4): poly_eval[(8, r)] = ev[(H.ADVICE, 0, r)]
+    phi_x, phi_nx, m_x = dbg["lookup_evals"][0]
+    poly_eval[(9, 0)] = m_x
+    poly_eval[(10, 0)], poly_eval[(10, 1)] = dbg["z_evals"][0][0], dbg["z_evals"][0][1]
+    poly_eval[(11, 0)], poly_eval[(11, 1)] = phi_x, phi_nx
+    poly_eval[(12, 0)] = dbg["random_eval"]
+
+    def lagrange(i):
+        wi = pow(omega, i % n, R)
+        return (xn - 1) * wi % R * pow(n * (x - wi) % R, -1, R) % R
+
+    def ev_expr(e):
+        (k, v), = e.items()
+        if k == "Constant": return P.from_mont(P.from_limbs(v), R)
+        if k == "Polynomial": return poly_eval[(v["poly"], v["rotation"])]
+        if k == "Challenge": return chal[v]
+        if k == "CommonPolynomial":
+            if v == "Identity": return x
+            return lagrange(v["Lagrange"])
+        if k == "Negated": return (-ev_expr(v)) % R
+        if k == "Sum": return (ev_expr(v[0]) + ev_expr(v[1])) % R
+        if k == "Product": return ev_expr(v[0]) * ev_expr(v[1]) % R
+        if k == "Scaled": return ev_expr(v[0]) * P.from_mont(P.from_limbs(v[1]), R) % R
+        if k == "DistributePowers":
+            exprs, base = v
+            b, acc = ev_expr(base), 0
+            for sub in exprs: acc = (acc * b + ev_expr(sub)) % R
+            return acc
+        raise ValueError(k)
+    assert ev_expr(golden["quotient_numerator"]) == dbg["numerator"]
