@@ -111,3 +111,17 @@ def test_numerator_formulas_match_snark_verifier_expression(setup, golden):
             return acc
         raise ValueError(k)
     assert ev_expr(golden["quotient_numerator"]) == dbg["numerator"]
+
+
+def test_fixture_instance_accumulator_passes_pairing(setup):
+    """The reference's own sanity check (aggregator/src/core.rs:75-89,129-140): the KZG accumulator carried in the first 12 instance
+    cells -- [lhs.x, lhs.y, rhs.x, rhs.y] as 3 limbs of 88 bits each (fe_to_limbs, LIMBS = 3, BITS = 88) -- satisfies
+    e(lhs, g2) == e(rhs, [s]g2).  Independent of the transcript and of the PLONK verifier."""
+    ref, pk, tis, instances, proof, spec, decide = setup
+    limbs = instances[0][:12]
+    assert all(v < (1 << 88) for v in limbs)
+    coords = [limbs[3 * i] + (limbs[3 * i + 1] << 88) + (limbs[3 * i + 2] << 176) for i in range(4)]
+    lhs, rhs = (coords[0], coords[1]), (coords[2], coords[3])
+    assert all(c < P.Q_MOD for c in coords) and P.g1_is_on_curve(lhs) and P.g1_is_on_curve(rhs)
+    assert decide(lhs, rhs)
+    assert not decide(P.g1_add(lhs, P.G1_GEN), rhs)
