@@ -21,7 +21,15 @@ def _worker(rank, world, port, fn, ret):
         dist.destroy_process_group()
 
 
-def run_world(fn, world=2, port=29611):
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def run_world(fn, world=2, port=None):
+    port = port or _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, fn, ret), nprocs=world, join=True)
@@ -45,7 +53,7 @@ def _msm_case(rank, world):
 
 
 def test_sharded_msm_combine_gloo():
-    res = run_world(_msm_case, 2, 29611)
+    res = run_world(_msm_case, 2)
     assert all(ok for ok, _ in res)
     assert res[0][1] == (0, 389) and res[1][1] == (389, 777)
 
@@ -91,7 +99,7 @@ def test_distributed_ntt_layout_gloo():
     import oracle_lib
     from util import rand_field
     from zkb200 import parallel
-    strips = run_world(_ntt_case, 2, 29612)
+    strips = run_world(_ntt_case, 2)
     orc = oracle_lib.load()
     x = rand_field(1 << 9, 77)
     full = orc.best_fft(x, orc.fr_omega(9), 9)
