@@ -190,7 +190,22 @@ def main():
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count - launches0
+    # nvidia-smi samples every 50 ms: a short timed region (small --steps) yields too few samples under load, so keep the same
+    # kernels running (untimed) until the load window is >= 1 s before stopping the sampler
+    extended = 0
+    try:
+        per_step_ms = max(ms_total / max(K, 1), 1e-3)
+        if ms_total < 1000.0:
+            extended = int(min(400, (1000.0 - ms_total) / per_step_ms + 1))
+            for _ in range(extended):
+                step_dev()
+            torch.cuda.synchronize()
+    except Exception:
+        extended = -1
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["load_window"] = "timed region" if extended == 0 else f"timed region + {extended} untimed identical steps"
     ms_step = ms_total / K
     value = world * 2 * BUTTERFLIES_PER_DIR / (ms_step * 1e-3)
 
