@@ -79,6 +79,45 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_proof_model(orc, shape, threads_note=""):
+    """CPU cost model of one create_proof on the host cores from MEASURED oracle primitives (the Rust prover cannot run here):
+    time one best_multiexp and one best_fft of the circuit's sizes with the oracle (all cores) and multiply by the number of
+    commitments / transforms halo2's create_proof performs for this shape (one MSM per committed polynomial, one size-n
+    iFFT per committed column, one extended (k + 3) FFT per polynomial entering the quotient, one extended iFFT).  Quotient
+    evaluation, permutation / lookup scans and witness generation are NOT included, so this is a lower bound of the CPU prover."""
+    import numpy as np
+    k, A, L, Pn = shape["k"], shape["advice_columns"], shape["lookup_arguments"], shape["permutation_columns"]
+    nf, d = shape.get("fixed_columns", 3), shape.get("cs_degree", 9)
+    n = 1 << k
+    nsets = (Pn + (d - 2) - 1) // (d - 2)
+    rng = np.random.default_rng(5)
+
+    def rand_fr(m):
+        a = rng.integers(0, 1 << 64, size=(m, 4), dtype=np.uint64)
+        a[:, 3] = rng.integers(0, 0x30644E72E131A029, size=m, dtype=np.uint64)
+        return a
+    # bases: multiples of the generator by small scalars are enough for timing (bucket additions dominate, not the points' values)
+    m_small = 1 << 12
+    small = orc.g1_fixed_base_mul(orc.g1_generator(), rand_fr(m_small))
+    bases = np.tile(small, (n // m_small, 1)) if n >= m_small else small[:n]
+    s = rand_fr(n)
+    orc.best_multiexp(s[:1 << 10], bases[:1 << 10])          # warm up the thread pool
+    t0 = time.perf_counter(); orc.best_multiexp(s, bases); t_msm = time.perf_counter() - t0
+    w = orc.fr_omega(k)
+    a = rand_fr(n)
+    orc.best_fft(a, w, k)
+    t0 = time.perf_counter(); orc.best_fft(a, w, k); t_fft = time.perf_counter() - t0
+    ek = k + 3
+    t_fft_ext = t_fft * ((1 << ek) * ek) / (n * k)          # scaled n log n (an extended transform at k = 23 needs GBs per call)
+    commits = A + 2 * L + nsets + 1 + (d - 1) + 2
+    iffts = A + 2 * L + nsets
+    ext_ffts = A + nf + Pn + nsets + 2 * L + 3
+    total = commits * t_msm + iffts * t_fft + (ext_ffts + 1) * t_fft_ext
+    return {"seconds_lower_bound": total, "msm_seconds": t_msm, "fft_seconds": t_fft, "extended_fft_seconds_scaled": t_fft_ext,
+            "commitments": commits, "iffts": iffts, "extended_ffts": ext_ffts + 1, "cores": orc.num_threads(),
+            "note": "measured oracle primitives x halo2 operation counts; excludes quotient evaluation, scans and witness generation"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm for the path (oracle best_fft restatement; the Rust crate cannot
     be built here: no cargo/rustc) on all host cores, same workload and metric."""
@@ -314,6 +353,12 @@ def main():
         cpu_baseline = {"value": 2 * BUTTERFLIES_PER_DIR / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                         "sample": "one full 2^24 fwd+inv round trip (2 x 201,326,592 butterflies), oracle best_fft, OpenMP all cores",
                         "seconds": dt}
+        # proof-level context: CPU lower bound for the k = 17 shape from measured primitives (about 10 s of CPU work)
+        try:
+            if "proof_keccak_shape_k17" in extras:
+                extras["proof_keccak_shape_k17"]["cpu_model"] = cpu_proof_model(orc, extras["proof_keccak_shape_k17"])
+        except Exception as e:
+            extras["cpu_model_error"] = repr(e)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
