@@ -100,3 +100,31 @@ def test_prove_verify_with_poseidon_transcript(kind, k):
     assert not ref.verify_proof(pk, tc.transcript_repr, tc.instances, proof)          # a Blake2b reader must not accept it
     proof_b, _ = ref.create_proof(pk, tc.transcript_repr, tc.instances, synth, blinds)
     assert proof_b != proof and len(proof_b) == len(proof)
+
+
+def test_keccak_and_evm_transcript():
+    """Keccak-f[1600] pinned by hashlib.sha3_256 (same permutation) and by the reference's KECCAK_CODE_HASH_EMPTY; the oracle prover
+    and verifier round-trip with snark-verifier's EVM transcript framing (uncompressed big-endian proof items)."""
+    import hashlib, random
+    import keccak_ref as K
+    rnd = random.Random(4)
+    for ln in (0, 1, 135, 136, 137, 300):
+        data = bytes(rnd.randrange(256) for _ in range(ln))
+        assert K.sha3_256(data) == hashlib.sha3_256(data).digest()
+    # eth-types/src/lib.rs KECCAK_CODE_HASH_EMPTY
+    assert K.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    tc = ThinCompressionShape(6, seed=31)
+    ref = H.Ref(tc.cs, 1234)
+    F = ref.F
+    pk = ref.keygen([F.arr(c) for c in tc.fixed_ints], tc.copies)
+    blinds = {"z": tc.blinds_ints["z"], "phi": tc.blinds_ints["phi"], "random_poly": F.arr(tc.blinds_ints["random_poly"])}
+    synth = lambda phase, ch: {c: F.arr(v) for c, v in tc.advice_ints(phase, ch).items()}
+    proof, _ = ref.create_proof(pk, tc.transcript_repr, tc.instances, synth, blinds, transcript=K.EvmTranscript(ref))
+    assert len(proof) == 11 * 64 + 17 * 32                       # uncompressed points, 32-byte scalars
+    assert ref.verify_proof(pk, tc.transcript_repr, tc.instances, proof, reader=K.EvmTranscript(proof=proof))
+    bad = bytearray(proof); bad[700] ^= 1
+    try:
+        ok = ref.verify_proof(pk, tc.transcript_repr, tc.instances, bytes(bad), reader=K.EvmTranscript(proof=bytes(bad)))
+    except AssertionError:
+        ok = False
+    assert not ok
