@@ -177,14 +177,23 @@ ZKB_API int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4], c
 /* Same with a choice of transcript: 0 = Blake2bWrite/Challenge255 (the reference's benches, circuit-benchmarks/src/super_circuit.rs:112),
  * 1 = snark-verifier-sdk PoseidonTranscript<NativeLoader> (gen_snark_shplonk, prover/src/common/prover/utils.rs:31): Poseidon T=5,
  * RATE=4, R_F=8, R_P=60 over Fr; points absorbed as (x mod r, y mod r).  The Poseidon restatement is pinned by the reference's own
- * chunk proof (tests/test_fixture_proof.py).                                                                                    */
+ * chunk proof (tests/test_fixture_proof.py);
+ * 2 = snark-verifier EvmTranscript<G1Affine, NativeLoader> over Keccak-256 (gen_evm_proof_shplonk, prover/src/common/prover/evm.rs:67):
+ * points absorbed AND written uncompressed as x || y big-endian (64 B), scalars 32 B big-endian, challenge = keccak256(buffer) mod r.   */
 ZKB_API int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const uint64_t transcript_repr[4],
                                    const uint64_t *const *instance_values, const uint32_t *instance_lens, zkb_session **out);
 /* Host-only transcript primitives (no CUDA device needed; used by the CPU test-suite to pin the session's hashers):
  * zkb_poseidon_hash_host        absorb n Fr (Montgomery) into a fresh PoseidonTranscript sponge, squeeze one challenge
- * zkb_blake2b_challenge_host    feed bytes to a fresh Blake2b("Halo2-Transcript") state, squeeze one Challenge255 (mod r)          */
+ * zkb_blake2b_challenge_host    feed bytes to a fresh Blake2b("Halo2-Transcript") state, squeeze one Challenge255 (mod r)
+ * zkb_keccak256_host            Keccak-256 of a byte string (the EvmTranscript hash; eth-types KECCAK_CODE_HASH_EMPTY is its "" digest)
+ * zkb_transcript_script_host    replay ops (0 common_scalar, 1 write_scalar, 2 write_point, 3 squeeze) through the session's transcript
+ *                               code of `kind`; operands in order (scalar 4 limbs, point 8 limbs, Montgomery); returns the proof bytes
+ *                               written and the squeezed challenges (4 limbs each); proof may be NULL to query the length          */
 ZKB_API int32_t zkb_poseidon_hash_host(const uint64_t *inputs, uint64_t n, uint64_t out[4]);
 ZKB_API int32_t zkb_blake2b_challenge_host(const uint8_t *bytes, uint64_t len, uint64_t out[4]);
+ZKB_API int32_t zkb_keccak256_host(const uint8_t *bytes, uint64_t len, uint8_t out[32]);
+ZKB_API int32_t zkb_transcript_script_host(int32_t kind, const uint8_t *ops, uint64_t n_ops, const uint64_t *operands, uint8_t *proof,
+                                           uint64_t cap, uint64_t *proof_len, uint64_t *challenges);
 ZKB_API int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const uint64_t *const *advice_columns,
                                        uint64_t *challenges_out);
 ZKB_API int32_t zkb_prove_finish(zkb_session *s, const uint64_t *z_blinds, const uint64_t *phi_blinds,

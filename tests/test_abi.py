@@ -160,3 +160,71 @@ def test_session_hashers_host_side(oracle):
         h = hashlib.blake2b(digest_size=64, person=b"Halo2-Transcript")
         h.update(data + b"\x00")
         assert P.from_mont(P.from_limbs(out), P.R_MOD) == int.from_bytes(h.digest(), "little") % P.R_MOD
+
+
+def test_transcript_framing_all_kinds(oracle):
+    """The session's own transcript code (zkb_transcript_script_host replays it without a device) against the oracle's three
+    transcripts on a scripted create_proof-like sequence: same proof bytes, same challenges.  Blake2b and Poseidon framing are also
+    covered end to end by the GPU proof tests; the EVM/Keccak framing is pinned by KECCAK_CODE_HASH_EMPTY + this."""
+    import ctypes, random
+    import numpy as np
+    import zkb200
+    import pyref as P
+    import halo2_ref as H
+    import keccak_ref as K
+    lib = zkb200.load_library()
+    rnd = random.Random(77)
+    vp = ctypes.c_void_p
+    for ln in (0, 1, 135, 136, 137, 500):                                        # the hash itself
+        data = bytes(rnd.randrange(256) for _ in range(ln))
+        out = (ctypes.c_uint8 * 32)()
+        buf = (ctypes.c_uint8 * max(1, ln)).from_buffer_copy(data or b"\0")
+        assert lib.zkb_keccak256_host(ctypes.cast(buf, vp) if ln else None, ln, ctypes.cast(out, vp)) == 0
+        assert bytes(out) == K.keccak256(data)
+    # script: repr, instances, then rounds of points / squeezes / scalars, with back-to-back squeezes (beta, gamma) as in create_proof
+    g = (1, 2)
+    def aff_limbs(pt):
+        return P.limbs(P.to_mont(pt[0], P.Q_MOD)) + P.limbs(P.to_mont(pt[1], P.Q_MOD))
+    pts = [aff_limbs(P.g1_mul(g, rnd.randrange(1, P.R_MOD))) for _ in range(9)]
+    ops, operands, script = [], [], []
+    def sc(kind):
+        v = rnd.randrange(P.R_MOD); ops.append(kind); operands.extend(P.limbs(P.to_mont(v, P.R_MOD))); script.append((kind, v))
+    def pt(i):
+        ops.append(2); operands.extend(int(x) for x in pts[i]); script.append((2, pts[i]))
+    def sq():
+        ops.append(3); script.append((3, None))
+    sc(0); sc(0); sc(0)
+    pt(0); pt(1); sq()
+    pt(2); sq(); sq()
+    pt(3); pt(4); pt(5); sq()
+    for _ in range(7): sc(1)
+    sq(); sq(); pt(6); sq(); sc(1); pt(7); sq(); sq(); sq(); pt(8)
+    n_sq = sum(1 for o in ops if o == 3)
+    opa = np.array(ops, dtype=np.uint8)
+    opd = np.array(operands, dtype=np.uint64)
+
+    class _O:                                                                     # the oracle transcripts only need g1_compress
+        def __init__(self, o): self.o = o
+    for kind, mk in ((0, lambda: H.Ref.Transcript(_O(oracle))), (1, lambda: H.Ref.PoseidonTranscript(_O(oracle))), (2, lambda: K.EvmTranscript())):
+        t = mk()
+        want_ch = []
+        for k, v in script:
+            if k == 0: t.common_scalar(v)
+            elif k == 1: t.write_scalar(v)
+            elif k == 2: t.write_point(np.array(v, dtype=np.uint64))
+            else: want_ch.append(t.squeeze())
+        plen = ctypes.c_uint64(0)
+        ch = np.zeros((n_sq, 4), dtype=np.uint64)
+        proof = (ctypes.c_uint8 * 4096)()
+        rc = lib.zkb_transcript_script_host(kind, vp(opa.ctypes.data), len(ops), vp(opd.ctypes.data), ctypes.cast(proof, vp), 4096,
+                                            ctypes.byref(plen), vp(ch.ctypes.data))
+        assert rc == 0
+        assert bytes(proof[: plen.value]) == bytes(t.buf), kind
+        assert [P.from_mont(P.from_limbs(c), P.R_MOD) for c in ch] == want_ch, kind
+    # identity points are refused by every kind, unknown kinds / ops too
+    bad = np.zeros(8, dtype=np.uint64)
+    one = np.array([2], dtype=np.uint8)
+    plen = ctypes.c_uint64(0)
+    for kind in (0, 1, 2):
+        assert lib.zkb_transcript_script_host(kind, vp(one.ctypes.data), 1, vp(bad.ctypes.data), None, 0, ctypes.byref(plen), None) != 0
+    assert lib.zkb_transcript_script_host(3, vp(one.ctypes.data), 0, None, None, 0, ctypes.byref(plen), None) != 0

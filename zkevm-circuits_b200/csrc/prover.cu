@@ -20,6 +20,7 @@
 #include "expr.cuh"
 #include "blake2b.h"
 #include "poseidon.h"
+#include "keccak.h"
 #include <algorithm>
 #include <memory>
 #include <string.h>
@@ -205,9 +206,12 @@ struct zkb_pk {
 
 struct zkb_session {
     zkb_pk *pk = nullptr;
-    int tkind = 0;  // 0: Blake2bWrite<_, G1Affine, Challenge255<_>> (benches), 1: snark-verifier-sdk PoseidonTranscript (gen_snark_shplonk)
+    // 0: Blake2bWrite<_, G1Affine, Challenge255<_>> (benches), 1: snark-verifier-sdk PoseidonTranscript (gen_snark_shplonk),
+    // 2: snark-verifier EvmTranscript over Keccak-256 (gen_evm_proof_shplonk)
+    int tkind = 0;
     Blake2b tr{"Halo2-Transcript"};
     PoseidonSponge pos;
+    std::vector<uint8_t> evm_buf;
     std::vector<uint8_t> proof;
     DevPool pool;
     std::vector<Fr *> inst_values, inst_polys, adv_values;
@@ -235,8 +239,15 @@ static Fr fq_canonical_to_fr(const Fq &c) {
     for (int i = 0; i < 8; ++i) out.l[i] = v[i];
     return fp_from_canonical(out);
 }
+// 32-byte big-endian image of a canonical field element (EvmTranscript absorbs and writes `to_repr()` reversed)
+template <class F>
+static void push_be32(std::vector<uint8_t> &dst, const F &canonical) {
+    const uint8_t *b = (const uint8_t *)canonical.l;
+    for (int i = 31; i >= 0; --i) dst.push_back(b[i]);
+}
 static void tr_common_scalar(zkb_session *s, const Fr &v) {
     if (s->tkind == 1) { s->pos.update(v); return; }
+    if (s->tkind == 2) { push_be32(s->evm_buf, fp_to_canonical(v)); return; }
     const uint8_t pre = 2;
     Fr c = fp_to_canonical(v);
     s->tr.update(&pre, 1);
@@ -245,12 +256,18 @@ static void tr_common_scalar(zkb_session *s, const Fr &v) {
 static void tr_write_scalar(zkb_session *s, const Fr &v) {
     tr_common_scalar(s, v);
     Fr c = fp_to_canonical(v);
+    if (s->tkind == 2) { push_be32(s->proof, c); return; }
     const uint8_t *b = (const uint8_t *)c.l;
     s->proof.insert(s->proof.end(), b, b + 32);
 }
 static int32_t tr_write_point(zkb_session *s, const G1Affine &p) {
     if (p.is_identity()) { set_error("cannot write points at infinity to the transcript"); return ZKB_ERR_STATE; }
     Fq x = fp_to_canonical(p.x), y = fp_to_canonical(p.y);
+    if (s->tkind == 2) {  // absorbed and written uncompressed: x || y, big-endian
+        push_be32(s->evm_buf, x); push_be32(s->evm_buf, y);
+        push_be32(s->proof, x); push_be32(s->proof, y);
+        return ZKB_OK;
+    }
     if (s->tkind == 1) {
         s->pos.update(fq_canonical_to_fr(x));
         s->pos.update(fq_canonical_to_fr(y));
@@ -267,6 +284,18 @@ static int32_t tr_write_point(zkb_session *s, const G1Affine &p) {
 }
 static Fr tr_squeeze(zkb_session *s) {
     if (s->tkind == 1) return s->pos.squeeze();
+    if (s->tkind == 2) {
+        // hash the buffer (plus a 0x01 byte when it holds just the previous digest), keep the digest as the new buffer,
+        // challenge = digest as a big-endian integer mod r
+        if (s->evm_buf.size() == 32) s->evm_buf.push_back(1);
+        uint8_t h[32];
+        keccak256(s->evm_buf.data(), s->evm_buf.size(), h);
+        s->evm_buf.assign(h, h + 32);
+        Fr v;
+        uint8_t *b = (uint8_t *)v.l;
+        for (int i = 0; i < 32; ++i) b[i] = h[31 - i];
+        return fp_mul(v, Fr::r2());  // Montgomery multiply reduces any 256-bit value: v * R^2 / R = v R mod r
+    }
     const uint8_t pre = 0;
     s->tr.update(&pre, 1);
     uint8_t h[64];
@@ -517,6 +546,57 @@ extern "C" int32_t zkb_poseidon_hash_host(const uint64_t *inputs, uint64_t n, ui
     memcpy(out, c.l, 32);
     return ZKB_OK;
 }
+// Host-only: replay a scripted sequence of transcript operations through the session's own transcript code (no device work).
+// ops[i]: 0 = common_scalar, 1 = write_scalar, 2 = write_point, 3 = squeeze_challenge; operands are consumed in order (scalar:
+// 4 limbs, point: 8 limbs, Montgomery form); challenges are appended to `challenges` (4 limbs each).  Lets the CPU suite pin the
+// framing of every transcript kind against the oracle's transcripts.
+extern "C" int32_t zkb_transcript_script_host(int32_t kind, const uint8_t *ops, uint64_t n_ops, const uint64_t *operands, uint8_t *proof, uint64_t cap,
+                                              uint64_t *proof_len, uint64_t *challenges) {
+    ZKB_ARG(kind >= 0 && kind <= 2 && (ops || n_ops == 0) && proof_len);
+    zkb_session s;  // no pk, no device pool: only the transcript members are touched
+    s.tkind = kind;
+    const uint64_t *op = operands;
+    for (uint64_t i = 0; i < n_ops; ++i) {
+        switch (ops[i]) {
+            case 0:
+            case 1: {
+                ZKB_ARG(op);
+                Fr v;
+                memcpy(v.l, op, 32);
+                op += 4;
+                if (ops[i] == 0) tr_common_scalar(&s, v); else tr_write_scalar(&s, v);
+                break;
+            }
+            case 2: {
+                ZKB_ARG(op);
+                G1Affine p;
+                memcpy(&p, op, 64);
+                op += 8;
+                ZKB_TRY(tr_write_point(&s, p));
+                break;
+            }
+            case 3: {
+                ZKB_ARG(challenges);
+                const Fr c = tr_squeeze(&s);
+                memcpy(challenges, c.l, 32);
+                challenges += 4;
+                break;
+            }
+            default: ZKB_ARG(false);
+        }
+    }
+    *proof_len = s.proof.size();
+    if (proof) {
+        ZKB_ARG(cap >= s.proof.size());
+        if (!s.proof.empty()) memcpy(proof, s.proof.data(), s.proof.size());
+    }
+    return ZKB_OK;
+}
+extern "C" int32_t zkb_keccak256_host(const uint8_t *bytes, uint64_t len, uint8_t out[32]) {
+    ZKB_ARG(out && (bytes || len == 0));
+    keccak256(bytes, len, out);
+    return ZKB_OK;
+}
 // feed raw bytes to a fresh Blake2b("Halo2-Transcript") state and squeeze one Challenge255 (prefix 0x00, 64-byte digest mod r)
 extern "C" int32_t zkb_blake2b_challenge_host(const uint8_t *bytes, uint64_t len, uint64_t out[4]) {
     ZKB_ARG(out && (bytes || len == 0));
@@ -615,7 +695,7 @@ extern "C" int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4]
 extern "C" int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const uint64_t transcript_repr[4], const uint64_t *const *instance_values,
                                       const uint32_t *instance_lens, zkb_session **out) {
     ZKB_ARG(pk && transcript_repr && out && (pk->cs.ni == 0 || (instance_values && instance_lens)));
-    ZKB_ARG(transcript_kind == 0 || transcript_kind == 1);
+    ZKB_ARG(transcript_kind >= 0 && transcript_kind <= 2);
     ZKB_CUDA(cudaSetDevice(pk->ctx->device));
     std::unique_ptr<zkb_session> s(new zkb_session());
     s->pk = pk;

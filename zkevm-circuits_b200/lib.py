@@ -60,6 +60,8 @@ SIGNATURES = {
     "zkb_prove_begin_ex": (ctypes.c_int32, [_vp, ctypes.c_int32, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "zkb_poseidon_hash_host": (ctypes.c_int32, [_vp, ctypes.c_uint64, _vp]),
     "zkb_blake2b_challenge_host": (ctypes.c_int32, [_vp, ctypes.c_uint64, _vp]),
+    "zkb_keccak256_host": (ctypes.c_int32, [_vp, ctypes.c_uint64, _vp]),
+    "zkb_transcript_script_host": (ctypes.c_int32, [ctypes.c_int32, _vp, ctypes.c_uint64, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
     "zkb_prove_advice_phase": (ctypes.c_int32, [_vp, ctypes.c_uint32, _vp, _vp]),
     "zkb_prove_finish": (ctypes.c_int32, [_vp, _vp, _vp, _vp, _vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
     "zkb_session_destroy": (ctypes.c_int32, [_vp]),

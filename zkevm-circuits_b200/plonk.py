@@ -149,12 +149,13 @@ class ProvingKey:
         except Exception: pass
 
 
-TRANSCRIPTS = {"blake2b": 0, "poseidon": 1}
+TRANSCRIPTS = {"blake2b": 0, "poseidon": 1, "evm": 2}
 
 
 def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blinds, random_poly, transcript="blake2b"):
     """Mirror of plonk::create_proof for one circuit; transcript = "blake2b" (Blake2bWrite, the reference's benches) or "poseidon"
-    (snark-verifier-sdk's PoseidonTranscript, what gen_snark_shplonk uses).
+    (snark-verifier-sdk's PoseidonTranscript, what gen_snark_shplonk uses) or "evm" (snark-verifier's EvmTranscript over Keccak-256,
+    what gen_evm_proof_shplonk uses; proof items uncompressed big-endian).
 
     transcript_repr: uint64[4] (Montgomery Fr).   instances: list of uint64 (len, 4) arrays (one per instance column).
     synthesize(phase, challenges) -> dict {advice column: uint64 (n,4) array, already blinded} for that phase's columns,
