@@ -71,6 +71,10 @@ ZKB_API int32_t zkb_ntt_fr_host(zkb_ctx *ctx, uint64_t *data_host, uint32_t log_
                         const uint64_t *scale /* 4 limbs or NULL */, int32_t coset_zeta);
 ZKB_API int32_t zkb_ntt_fr_dev(zkb_ctx *ctx, uint64_t *data_dev, uint32_t log_n, const uint64_t omega[4],
                        const uint64_t *scale /* HOST pointer, 4 limbs or NULL */, int32_t coset_zeta, void *stream);
+/* `count` in-place transforms of one size through ONE kernel launch per pass (all columns of a prover stage): cols_dev is a HOST
+ * array of `count` device pointers.                                                                                              */
+ZKB_API int32_t zkb_ntt_fr_batch_dev(zkb_ctx *ctx, uint64_t *const *cols_dev, uint32_t count, uint32_t log_n, const uint64_t omega[4],
+                                     const uint64_t *scale /* HOST pointer or NULL */, int32_t coset_zeta, void *stream);
 /* omega_k = Fr::ROOT_OF_UNITY^(2^(28-k)) and its inverse (EvaluationDomain::new); host-side helper. */
 ZKB_API int32_t zkb_fr_root_of_unity(uint32_t k, uint64_t omega[4], uint64_t omega_inv[4]);
 
@@ -89,11 +93,39 @@ ZKB_API int32_t zkb_msm_g1_batch_dev(zkb_ctx *ctx, const uint64_t *const *scalar
                                      const uint64_t *bases_dev, uint64_t n, uint64_t *out_affine, void *stream);
 /* Number of bucket additions + reduction additions the last MSM on this context performed (G1-adds metric). */
 ZKB_API uint64_t zkb_msm_last_adds(const zkb_ctx *ctx);
+/* Bucket-reduction levels beyond the first that the last MSM actually executed (decided on the device, no host round trip). */
+ZKB_API uint32_t zkb_msm_last_levels(const zkb_ctx *ctx);
 
 /* out[i] = [scalars[i]] * base, affine outputs (device buffers).  Used for ParamsKZG::setup / unsafe_setup_with_s
  * (g[i] = [s^i] G) and to synthesise distinct benchmark bases.                                                  */
 ZKB_API int32_t zkb_g1_fixed_base_mul_dev(zkb_ctx *ctx, const uint64_t base_affine_host[8], const uint64_t *scalars_dev,
                                   uint64_t n, uint64_t *out_affine_dev, void *stream);
+
+/* ---- SRS handle: ParamsKZG<Bn256> resident on the device ---------------------------------------------------------------
+ * Replaces the prover-facing part of halo2_proofs::poly::kzg::commitment::ParamsKZG (src/poly/kzg/commitment.rs): the
+ * reference loads one params file per degree (prover/src/utils.rs load_params, prover/src/common/prover.rs:37-57) and
+ * `downsize`s it for smaller circuits (prover/src/common/prover.rs:54-55, aggregator/src/recursion/util.rs:156).
+ * zkb_srs_load       upload g / g_lagrange (2^k x 64 B each, halo2curves G1Affine layout) ONCE per context; g_lagrange may be
+ *                    NULL: it is then derived on the device by the inverse FFT over G1 (`g_to_lagrange`).  Memory permitting
+ *                    (ZKB_MSM_SHIFT_GB, default 24) the window-shifted copies 2^(c w) P_i of both bases are built, which turns
+ *                    every commitment into ONE bucket set with no Horner pass (msm.cu).
+ * zkb_srs_downsize   ParamsKZG::downsize(new_k): g truncated to 2^new_k, g_lagrange recomputed; the source handle stays valid.
+ * zkb_srs_commit_*   ParamsKZG::commit (basis 0, coefficients against g) / commit_lagrange (basis 1, values against g_lagrange);
+ *                    n <= 2^k scalars; the result is normalised like zkb_msm_g1_*.
+ * zkb_srs_read       copy one basis back to the host (tests, writing a downsized params file).                                    */
+typedef struct zkb_srs zkb_srs;
+ZKB_API int32_t zkb_srs_load(zkb_ctx *ctx, uint32_t k, const uint64_t *g_host, const uint64_t *g_lagrange_host, zkb_srs **out);
+ZKB_API int32_t zkb_srs_load_dev(zkb_ctx *ctx, uint32_t k, const uint64_t *g_dev, const uint64_t *g_lagrange_dev, zkb_srs **out);
+ZKB_API int32_t zkb_srs_destroy(zkb_srs *srs);
+ZKB_API uint32_t zkb_srs_k(const zkb_srs *srs);
+ZKB_API int32_t zkb_srs_downsize(zkb_srs *srs, uint32_t new_k, zkb_srs **out);
+ZKB_API int32_t zkb_srs_read(zkb_srs *srs, int32_t basis, uint64_t *out_host);
+ZKB_API int32_t zkb_srs_commit_dev(zkb_srs *srs, int32_t basis, const uint64_t *scalars_dev, uint64_t n, uint64_t out_affine[8],
+                                   uint8_t *out_compressed, void *stream);
+ZKB_API int32_t zkb_srs_commit_host(zkb_srs *srs, int32_t basis, const uint64_t *scalars_host, uint64_t n, uint64_t out_affine[8],
+                                    uint8_t *out_compressed);
+ZKB_API int32_t zkb_srs_commit_batch_dev(zkb_srs *srs, int32_t basis, const uint64_t *const *scalar_cols_dev, uint32_t batch, uint64_t n,
+                                         uint64_t *out_affine, void *stream);
 
 /* ---- element-wise field kernels (device buffers); field: 0 = Fr, 1 = Fq ------------------------------------
  * op: 0 add, 1 sub, 2 mul (binary);  unary op: 0 invert (0 -> 0), 1 canonical->Montgomery, 2 Montgomery->canonical,
@@ -161,11 +193,27 @@ ZKB_API int32_t zkb_comm_destroy(zkb_ctx *ctx);
  *                    challenges squeezed after that phase in challenges_out[num_challenges][4] (Montgomery Fr)
  * zkb_prove_finish   lookups -> permutation -> vanishing -> quotient -> evaluations -> SHPLONK; z_blinds
  *                    [n_sets][bf], phi_blinds [n_lookups][bf], random_poly [n] are Montgomery Fr arrays on the host.
- *                    proof_out may be NULL to query the length.                                                       */
+ *                    The first call runs the proof and keeps its bytes in the session: proof_out may be NULL (query the length) or
+ *                    too short (ZKB_ERR_ARG, *proof_len set) -- call again with a buffer of *proof_len bytes; later calls only copy.
+ *                    Multi-GPU sessions (zkb_comm_init): every zkb_pk_* / zkb_prove_* call, zkb_pk_vk_bytes included, is a COLLECTIVE
+ *                    over the communicator and must be issued by all ranks in the same order; a rank-local failure (allocation, CUDA
+ *                    error) leaves the other ranks inside a collective, so abort the job on any non-zero return.                  */
 typedef struct zkb_pk zkb_pk;
 typedef struct zkb_session zkb_session;
 ZKB_API int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
                               const uint64_t *const *sigma_values, const uint64_t *g, const uint64_t *g_lagrange, zkb_pk **out);
+/* Same against a loaded SRS handle (shared by every pk of the context; srs->k must equal the circuit's k: downsize first). */
+ZKB_API int32_t zkb_pk_create_with_srs(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
+                                       const uint64_t *const *sigma_values, zkb_srs *srs, zkb_pk **out);
+/* keygen_pk2 / keygen_vk + keygen_pk (halo2_proofs plonk/keygen.rs; reference call site prover/src/common/prover/utils.rs:43-61,
+ * :55): the caller runs Circuit::synthesize in keygen mode and hands over the fixed column values and the COPY CONSTRAINTS
+ * (n_copies x 4 u32: left column, left row, right column, right row; columns index the CSF's permutation column list).  The
+ * permutation Assembly (cycle merging, permutation/keygen.rs) runs on the host, the sigma columns delta^col * omega^row, every
+ * polynomial / coset form and the vk commitments (zkb_pk_vk_bytes) are produced on the device.                                   */
+ZKB_API int32_t zkb_keygen_pk(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
+                              const uint32_t *copies, uint64_t n_copies, zkb_srs *srs, zkb_pk **out);
+/* sigma column `column` of a proving key (Lagrange values, 2^k x 32 B) back to the host. */
+ZKB_API int32_t zkb_pk_sigma_read(zkb_pk *pk, uint32_t column, uint64_t *out_host);
 ZKB_API int32_t zkb_pk_destroy(zkb_pk *pk);
 /* VerifyingKey bytes in SerdeFormat::Processed layout (u32 BE k || u32 BE num_fixed || fixed || permutation commitments,
  * compressed points; the layout of the reference fixture's vk).  out may be NULL to query the length.                     */

@@ -51,7 +51,7 @@ def test_batch_invert(A, oracle):
     assert (got == oracle.fr_inv(a)).all()
 
 
-@pytest.mark.parametrize("log_n", list(range(0, 15)) + [16, 17, 20])
+@pytest.mark.parametrize("log_n", list(range(0, 15)) + [16, 17, 20, 21, 22, 23])
 def test_ntt_vs_oracle(A, oracle, log_n):
     a = rand_field(1 << log_n, 100 + log_n)
     w, wi = A.root_of_unity(log_n)
@@ -109,6 +109,39 @@ def test_ntt_2_24_roundtrip_and_linearity(A, oracle):
     for k in (0, 1, 2, 77777, n - 1):
         wk = oracle.fr_pow(w, (j0 * k) % n)
         assert (fd[k] == oracle.fr_mul(aj[None], wk[None])[0]).all()
+
+
+@pytest.mark.parametrize("log_n", [24, 25, 26])
+def test_ntt_full_size_vs_oracle(A, oracle, log_n):
+    """BASELINE config #2 (2^24) and the sizes of the three-pass plan (2^25, 2^26: config #5's domain) compared ELEMENT BY ELEMENT
+    with the oracle's best_fft restatement -- forward, and inverse with the fused 1/n."""
+    import torch
+    n = 1 << log_n
+    w, wi = A.root_of_unity(log_n)
+    ninv = oracle.fr_inv(oracle.fr_from_canonical(np.array([[n, 0, 0, 0]], dtype=np.uint64)))[0]
+    a = A.random_fr_dev(n, 9000 + log_n)
+    ha = to_host(a)
+    f = A.best_fft_dev(a.clone(), w, log_n)
+    exp = oracle.best_fft(ha, w, log_n)
+    assert (to_host(f) == exp).all()
+    del exp
+    back = A.best_fft_dev(f, wi, log_n, scale=ninv)
+    assert torch.equal(back, a)
+    if log_n == 24:
+        inv = A.best_fft_dev(a.clone(), wi, log_n, scale=ninv)
+        exp = oracle.fr_mul(oracle.best_fft(ha, wi, log_n), np.repeat(ninv[None], n, axis=0))
+        assert (to_host(inv) == exp).all()
+
+
+def test_ntt_batch_columns(A, oracle):
+    """several columns through one launch per pass (how the prover transforms a stage's columns), distinct buffers"""
+    from zkb200 import poly as Pz
+    log_n = 14
+    w, _ = A.root_of_unity(log_n)
+    cols = [rand_field(1 << log_n, 640 + i) for i in range(5)]
+    got = Pz.ntt_batch_dev([to_dev(c) for c in cols], w, log_n)
+    for c, g in zip(cols, got):
+        assert (to_host(g) == oracle.best_fft(c, w, log_n)).all()
 
 
 def make_bases(A, oracle, n, seed):
@@ -239,3 +272,46 @@ def test_msm_2_23_linearity(A, oracle):
     hb, ha = to_host(bases), to_host(a)
     exp = oracle.g1_to_affine(oracle.best_multiexp(np.stack([ha[i] for i in idx]), np.stack([hb[i] for i in idx])))
     assert (r.affine == exp).all()
+
+
+def test_msm_reduction_levels_decided_on_device(A, oracle):
+    """random scalars: the chunked level 0 leaves at most a few partials per bucket (one extra level); a column whose scalars are all
+    equal piles everything into one bucket per window and needs more levels -- the host never learns the counts."""
+    from zkb200 import default_context
+    n = 1 << 16
+    bases = make_bases(A, oracle, n, 777)
+    bt = to_dev(bases)
+    r = A.best_multiexp_dev(to_dev(rand_field(n, 778)), bt)
+    lv_random = default_context().lib.zkb_msm_last_levels(default_context().handle)
+    same = np.repeat(rand_field(1, 779), n, axis=0)
+    r2 = A.best_multiexp_dev(to_dev(same), bt)
+    lv_skew = default_context().lib.zkb_msm_last_levels(default_context().handle)
+    assert (r2.affine == oracle.g1_to_affine(oracle.best_multiexp(same, bases))).all()
+    assert lv_random <= 1 and lv_skew >= 2
+
+
+@pytest.mark.parametrize("k", [6, 10])
+def test_srs_handle_commit_and_downsize(A, oracle, k):
+    """zkb_srs_*: commit / commit_lagrange against the loaded handle == oracle best_multiexp; ParamsKZG::downsize on the device
+    (group iFFT of the truncated g) == the oracle's trapdoor construction [L_i(s)] G of the smaller SRS, point for point."""
+    import halo2_ref as H
+    from zkb200.params import ParamsKZG
+    s = 31337
+    ref = H.Ref(H.ConstraintSystem(k, 0, 1, 0).finalize(), s)
+    params = ParamsKZG(k, ref.g, ref.g_lagrange)
+    srs = params.load()
+    assert srs.k == k
+    v = rand_field(1 << k, 50 + k)
+    assert (srs.commit_lagrange(to_dev(v)).affine == ref.commit_lagrange(v)).all()
+    assert (srs.commit(to_dev(v)).affine == ref.commit(v)).all()
+    short = rand_field((1 << k) - 5, 51 + k)
+    assert (srs.commit(to_dev(short)).affine == ref.commit(short)).all()
+    # g_lagrange derived on the device from g alone
+    srs2 = ParamsKZG(k, ref.g, None).load(derive_lagrange=True)
+    assert (srs2.read(1) == ref.g_lagrange).all()
+    small = srs.downsize(k - 2)
+    ref_small = H.Ref(H.ConstraintSystem(k - 2, 0, 1, 0).finalize(), s)
+    assert (small.read(0) == ref_small.g).all()
+    assert (small.read(1) == ref_small.g_lagrange).all()
+    vs = rand_field(1 << (k - 2), 52 + k)
+    assert (small.commit_lagrange(to_dev(vs)).affine == ref_small.commit_lagrange(vs)).all()

@@ -128,3 +128,71 @@ def test_create_proof_poseidon_transcript_matches_oracle(kind, k):
     proof = Z.create_proof(pk, F.arr([tc.transcript_repr])[0], [F.arr(c) for c in tc.instances], synth, zb, pb, rp, transcript="poseidon")
     assert first_diff(proof, proof_ref) is None, f"first differing 32-byte proof item: {first_diff(proof, proof_ref)}"
     assert ref.verify_proof(pkr, tc.transcript_repr, tc.instances, proof, reader=H.Ref.PoseidonReader(proof))
+
+
+@pytest.mark.parametrize("k", [5, 8])
+def test_keygen_pk_matches_oracle_keygen(k):
+    """zkb_keygen_pk: permutation assembly from the copy constraints + sigma columns on the device == the oracle's restated
+    keygen (plonk/permutation/keygen.rs), vk bytes identical to the host-sigma path, and the pk proves byte-identically."""
+    from zkb200 import plonk as Z
+    from zkb200.params import ParamsKZG
+    tc = ToyCircuit(k, seed=300 + k)
+    ref = H.Ref(tc.cs, 1234)
+    F = ref.F
+    fixed = [F.arr(c) for c in tc.fixed_ints]
+    pkr = ref.keygen(fixed, tc.copies)
+    cidx = {c: i for i, c in enumerate(tc.cs.perm_columns)}
+    copies = [(cidx[(lt, lc)], lr, cidx[(rt, rc)], rr) for (lt, lc, lr), (rt, rc, rr) in tc.copies]
+    srs = ParamsKZG(k, ref.g, ref.g_lagrange).load()
+    zcs = to_product_cs(tc.cs, ref.bf, ref.d)
+    pk = Z.ProvingKey(zcs, fixed, None, srs=srs, copies=copies)
+    for i in range(len(tc.cs.perm_columns)):
+        assert (pk.sigma_values(i) == pkr["sigma_values"][i]).all(), f"sigma column {i}"
+    pk_host = Z.ProvingKey(zcs, fixed, pkr["sigma_values"], srs=srs)        # two keys share one SRS handle
+    assert pk.vk_bytes() == pk_host.vk_bytes()
+    exp_vk = k.to_bytes(4, "big") + len(fixed).to_bytes(4, "big") + b"".join(ref.o.g1_compress(c) for c in pkr["fixed_commitments"] + pkr["sigma_commitments"])
+    assert pk.vk_bytes() == exp_vk
+    rp = F.arr(tc.blinds_ints["random_poly"])
+    blinds = {"z": tc.blinds_ints["z"], "phi": tc.blinds_ints["phi"], "random_poly": rp}
+    proof_ref, _ = ref.create_proof(pkr, tc.transcript_repr, tc.instances, lambda ph, ch: {c: F.arr(v) for c, v in tc.advice_ints(ph, ch).items()}, blinds)
+
+    def synth(phase, ch):
+        chi = {i: F.ints(v[None])[0] for i, v in ch.items()}
+        return {c: F.arr(v) for c, v in tc.advice_ints(phase, chi).items()}
+    zb = np.concatenate([F.arr(b) for b in tc.blinds_ints["z"]]) if tc.blinds_ints["z"] else None
+    pb = np.concatenate([F.arr(b) for b in tc.blinds_ints["phi"]]) if tc.blinds_ints["phi"] else None
+    proof = Z.create_proof(pk, F.arr([tc.transcript_repr])[0], [F.arr(c) for c in tc.instances], synth, zb, pb, rp)
+    assert proof == proof_ref
+
+
+def test_prove_finish_query_then_fetch():
+    """header contract: proof_out == NULL queries the length, a short buffer fails WITHOUT losing the proof, a second call copies it"""
+    import ctypes
+    from zkb200 import plonk as Z
+    from zkb200.lib import check
+    tc = GatesOnlyCircuit(5, seed=3)
+    ref = H.Ref(tc.cs, 1234)
+    F = ref.F
+    fixed = [F.arr(c) for c in tc.fixed_ints]
+    pkr = ref.keygen(fixed, tc.copies)
+    pk = Z.ProvingKey(to_product_cs(tc.cs, ref.bf, ref.d), fixed, pkr["sigma_values"], ref.g, ref.g_lagrange)
+    lib = pk.ctx.lib
+    tr = np.ascontiguousarray(F.arr([tc.transcript_repr])[0])
+    sess = ctypes.c_void_p()
+    check(lib.zkb_prove_begin(pk.handle, ctypes.c_void_p(tr.ctypes.data), None, None, ctypes.byref(sess)))
+    cols = {c: np.ascontiguousarray(F.arr(v)) for c, v in tc.advice_ints(0, {}).items()}
+    tbl = (ctypes.c_void_p * tc.cs.num_advice)(*[cols[c].ctypes.data for c in range(tc.cs.num_advice)])
+    check(lib.zkb_prove_advice_phase(sess, 0, ctypes.cast(tbl, ctypes.c_void_p), None))
+    rp = np.ascontiguousarray(F.arr(tc.blinds_ints["random_poly"]))
+    zb = np.ascontiguousarray(np.concatenate([F.arr(b) for b in tc.blinds_ints["z"]])) if tc.blinds_ints["z"] else None
+    n = ctypes.c_uint64(0)
+    check(lib.zkb_prove_finish(sess, ctypes.c_void_p(zb.ctypes.data) if zb is not None else None, None, ctypes.c_void_p(rp.ctypes.data), None, 0, ctypes.byref(n)))
+    assert n.value > 0
+    small = (ctypes.c_uint8 * 8)()
+    assert lib.zkb_prove_finish(sess, None, None, None, ctypes.cast(small, ctypes.c_void_p), 8, ctypes.byref(n)) != 0
+    out = (ctypes.c_uint8 * n.value)()
+    check(lib.zkb_prove_finish(sess, None, None, None, ctypes.cast(out, ctypes.c_void_p), n.value, ctypes.byref(n)))
+    lib.zkb_session_destroy(sess)
+    blinds = {"z": tc.blinds_ints["z"], "phi": tc.blinds_ints["phi"], "random_poly": F.arr(tc.blinds_ints["random_poly"])}
+    proof_ref, _ = ref.create_proof(pkr, tc.transcript_repr, tc.instances, lambda ph, ch: {c: F.arr(v) for c, v in tc.advice_ints(ph, ch).items()}, blinds)
+    assert bytes(out) == proof_ref

@@ -33,6 +33,12 @@ def _cur_stream():
     return _vp(s if s else 1)
 
 
+def sync_current_stream():
+    """wait for torch's current stream (entry points that work on the context's own stream read tensors torch produced)"""
+    import torch
+    torch.cuda.current_stream().synchronize()
+
+
 def root_of_unity(k):
     """(omega, omega_inv) of the 2^k domain: Fr::ROOT_OF_UNITY^(2^(28-k)) (EvaluationDomain::new)."""
     from .lib import load_library

@@ -38,18 +38,20 @@ void set_error(const char *fmt, ...);
         }                                                                        \
     } while (0)
 
-// One cached NTT plan per (log_n, omega): twiddle tables on the device.
+// One cached NTT plan per (log_n, omega): twiddle tables on the device (see ntt.cu for the tile / pass structure).
 struct NttPlan {
     uint32_t log_n = 0;
     int npass = 0;
     int bits[3] = {0, 0, 0};
-    Fr *tw_lo = nullptr;   // omega^i,           i < 2^min(log_n, 12)
-    Fr *tw_hi = nullptr;   // omega^(i * 2^12),  i < 2^(log_n - 12)   (log_n > 12)
-    Fr *loc[3] = {nullptr, nullptr, nullptr};  // per pass: (omega_{2^a})^i, i < 2^(a-1)
-    // two-pass plans up to 2^25: the complete inter-pass twiddle table T[j_in * A + k] = omega^(j_in k) (x scale), n entries,
-    // so the boundary costs ONE multiply per element instead of two (lo x hi combine + apply)
-    Fr *tw_full = nullptr;
-    Fr *tw_full_scaled = nullptr;
+    Fr *tw_lo = nullptr;   // omega^i,           i < 2^min(log_n, 12)   (source of the boundary tables)
+    Fr *tw_hi = nullptr;   // omega^(i * 2^12),  i < 2^(log_n - 12)     (log_n > 12)
+    Fr *loc[3] = {nullptr, nullptr, nullptr};  // per pass: (omega_{2^a})^i, i < 2^(a-1); TMA-staged into shared memory once per CTA
+    // inter-pass twiddle tables, one per pass boundary, stored TILE-MAJOR in the order the consuming tile reads them
+    // (tile = cblk, then bit-reversed row q, then column c) so that one cp.async.bulk stages a tile's 64 KB of twiddles:
+    //   boundary p: 2^(bits[p]) * 2^(log_inner_p) entries = n for the first boundary, A2*A3 for the second of a 3-pass plan.
+    Fr *tw_b[2] = {nullptr, nullptr};
+    // the LAST boundary's table with a caller scale folded in (1/n of the inverse transforms), rebuilt when the scale changes
+    Fr *tw_b_scaled = nullptr;
     Fr scaled_key;
     bool has_scaled = false;
 };
@@ -70,7 +72,9 @@ struct zkb_ctx {
     void *nccl_comm = nullptr;
     int rank = 0, nranks = 1;
     uint64_t launches = 0;
+    bool ntt_ready = false;   // per-device kernel attributes / constants of ntt.cu are set (a context owns one device)
     uint64_t msm_last_adds = 0;
+    uint32_t msm_last_levels = 0;   // reduction levels >= 1 the last MSM actually executed (device-side decision)
     std::map<std::array<uint64_t, 5>, zkb::NttPlan> ntt_plans;
     // grow-only scratch arenas (device), keyed by purpose; avoids cudaMalloc in steady state
     zkb::DeviceBuffer scratch[12];
@@ -80,6 +84,17 @@ struct zkb_ctx {
     size_t block_cache_bytes = 0;
     void *pinned = nullptr;  // small pinned staging buffer
     size_t pinned_bytes = 0;
+};
+
+// ParamsKZG<Bn256> resident on the device (srs.cu): g (monomial basis), g_lagrange, and -- memory permitting -- the
+// window-shifted copies the one-bucket-set Pippenger variant gathers from.  One handle per context, shared by proving keys.
+struct zkb_srs {
+    zkb_ctx *ctx = nullptr;
+    uint32_t k = 0;
+    uint64_t n = 0;
+    zkb::G1Affine *g = nullptr, *g_lagrange = nullptr;
+    zkb::G1Affine *g_shift = nullptr, *g_lagrange_shift = nullptr;   // msm_shift_copies(n) x n points each, or null
+    std::vector<std::pair<void *, size_t>> blocks;
 };
 
 namespace zkb {
@@ -96,8 +111,8 @@ Fr host_zeta();
 // dst <- NTT_omega(src * in_scale) * scale ; src == dst allowed; coset_zeta as in zkb_ntt_fr_dev
 int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src, Fr *dst, uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta,
                       const Fr *d_in_scale, cudaStream_t st);
-// `count` transforms in one launch per pass: column y reads d_src_tbl[y], writes d_dst_tbl[y] (device pointer tables)
-int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *src, Fr *dst, const Fr *const *d_src_tbl, Fr *const *d_dst_tbl, uint32_t count, uint32_t log_n,
+// `count` transforms in one launch per pass: column y reads h_src[y], writes h_dst[y] (HOST arrays of device pointers; may alias)
+int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_dst, uint32_t count, uint32_t log_n,
                             const Fr &omega, const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, cudaStream_t st);
 // synchronises: the result point is returned to the host
 int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, uint64_t n, G1Affine *out_affine_host, cudaStream_t st);
@@ -110,6 +125,10 @@ int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uin
                                G1Affine *out_affine_host, bool shifted, cudaStream_t st);
 int32_t msm_g1_batch_device(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uint32_t batch, const G1Affine *bases, uint64_t n,
                             G1Affine *out_affine_host, cudaStream_t st);
+// SRS handle (srs.cu): sources on the host or on the device; g_lagrange == nullptr -> derived on the device (g_to_lagrange)
+int32_t srs_create(zkb_ctx *ctx, uint32_t k, const G1Affine *g, bool g_on_device, const G1Affine *g_lagrange, bool gl_on_device, zkb_srs **out);
+// `count` commitments against basis 0 (g) / 1 (g_lagrange); cols = HOST array of device pointers; synchronises (results on the host)
+int32_t srs_commit_many(zkb_srs *s, int basis, const Fr *const *cols, uint32_t count, uint64_t len, G1Affine *out_host, cudaStream_t st);
 int32_t fr_powers_device(zkb_ctx *ctx, const Fr &base, uint64_t n, Fr *out, cudaStream_t st);
 int32_t poly_eval_device(zkb_ctx *ctx, const Fr *const *d_polys, uint32_t num, uint64_t n, const Fr &x, Fr *out_host, cudaStream_t st);
 int32_t prefix_product_device(zkb_ctx *ctx, const Fr *in, uint64_t n, const Fr &init, Fr *out, cudaStream_t st);
@@ -120,5 +139,22 @@ int32_t batch_invert_device(zkb_ctx *ctx, const Fr *a, Fr *out, uint64_t n, cuda
 // in-place u64 sum across the context's ranks (exact gather when the supports are disjoint); no-op for a single rank
 int32_t comm_allreduce_u64(zkb_ctx *ctx, void *dev_buf, size_t count, cudaStream_t st);
 
-enum ScratchSlot { SCR_NTT = 0, SCR_MSM_A = 1, SCR_MSM_B = 2, SCR_MSM_C = 3, SCR_HOSTIO_A = 4, SCR_HOSTIO_B = 5, SCR_MISC = 6, SCR_MISC2 = 7, SCR_MSM_TBL = 8, SCR_COMM = 9 };
+struct DevPool {  // owns device allocations of a pk / session; blocks are recycled through the context's block cache
+    zkb_ctx *ctx = nullptr;
+    std::vector<std::pair<void *, size_t>> ptrs;
+    ~DevPool() {
+        if (!ctx) return;
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &p : ptrs) block_free(ctx, p.first, p.second);
+    }
+    int32_t alloc(size_t bytes, void **out) {
+        size_t got = 0;
+        ZKB_TRY(block_alloc(ctx, bytes ? bytes : 32, out, &got));
+        ptrs.push_back({*out, got});
+        return ZKB_OK;
+    }
+    int32_t fr(uint64_t n, Fr **out) { return alloc(n * sizeof(Fr), (void **)out); }
+};
+
+enum ScratchSlot { SCR_NTT = 0, SCR_MSM_A = 1, SCR_MSM_B = 2, SCR_MSM_C = 3, SCR_HOSTIO_A = 4, SCR_HOSTIO_B = 5, SCR_MISC = 6, SCR_MISC2 = 7, SCR_MSM_TBL = 8, SCR_COMM = 9, SCR_NTT_DESC = 10, SCR_MSM_D = 11 };
 }  // namespace zkb

@@ -74,7 +74,7 @@ void block_free(zkb_ctx *ctx, void *p, size_t bytes) {
 using namespace zkb;
 
 extern "C" const char *zkb_last_error(void) { return g_err; }
-extern "C" uint32_t zkb_version(void) { return (1u << 16) | 0u; }
+extern "C" uint32_t zkb_version(void) { return (1u << 16) | 1u; }
 
 extern "C" int32_t zkb_init(int32_t device, zkb_ctx **out) {
     ZKB_ARG(out != nullptr);
@@ -110,8 +110,9 @@ extern "C" int32_t zkb_destroy(zkb_ctx *ctx) {
         NttPlan &p = kv.second;
         if (p.tw_lo) cudaFree(p.tw_lo);
         if (p.tw_hi) cudaFree(p.tw_hi);
-        if (p.tw_full) cudaFree(p.tw_full);
-        if (p.tw_full_scaled) cudaFree(p.tw_full_scaled);
+        for (int i = 0; i < 2; ++i)
+            if (p.tw_b[i]) cudaFree(p.tw_b[i]);
+        if (p.tw_b_scaled) cudaFree(p.tw_b_scaled);
         for (int i = 0; i < 3; ++i)
             if (p.loc[i]) cudaFree(p.loc[i]);
     }
@@ -127,6 +128,7 @@ extern "C" int32_t zkb_destroy(zkb_ctx *ctx) {
 
 extern "C" uint64_t zkb_launch_count(const zkb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint64_t zkb_msm_last_adds(const zkb_ctx *ctx) { return ctx ? ctx->msm_last_adds : 0; }
+extern "C" uint32_t zkb_msm_last_levels(const zkb_ctx *ctx) { return ctx ? ctx->msm_last_levels : 0; }
 extern "C" void *zkb_stream(zkb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" int32_t zkb_sync(zkb_ctx *ctx) {
     ZKB_ARG(ctx);

@@ -10,13 +10,17 @@
 //      1..2^(c-1) per window) -- coalesced 32-byte loads, one thread per scalar;
 //   2. a counting sort (histogram -> scan -> scatter) groups point indices by (window, |digit|): 4 bytes per
 //      (point, window) pair, no 64-byte point ever moves;
-//   3. one thread per bucket accumulates its points with mixed XYZZ additions (8M + 2S), gathering bases by index
-//      (a base is two 32-byte sectors);
+//   3. the sorted (bucket-major) pair list is cut into CHUNKS of exactly 32 entries, one thread per chunk, regardless of bucket
+//      boundaries: every lane of a warp performs the same 32 mixed XYZZ additions (8M + 2S, bases gathered by index, a base is
+//      two 32-byte sectors) and flushes one partial sum per bucket it crossed; the partials of a bucket are then reduced by
+//      levels of <= 64-entry tasks.  No step between the digit kernels and the final window sums returns to the host: task
+//      arrays are sized from bounds, and the reduction levels that turn out to be unnecessary exit on a device-side flag;
 //   4. each window's buckets are reduced by segmented running sums (all windows and segments in parallel), the
 //      segment partials are tree-reduced per window, and the W window sums are combined by Horner doubling.
 //   Work is dominated by n*W mixed additions = n*W*10 Fq multiplies: bound by the integer-multiply pipe.
 #include "common.cuh"
 #include <string.h>
+#include <algorithm>
 
 namespace zkb {
 
@@ -142,6 +146,51 @@ __global__ void scan_add_kernel(uint32_t *__restrict__ out, const uint32_t *__re
         if (base + k < n) out[base + k] += add;
 }
 
+// the same three kernels for the gated reduction levels: the scan of tcount goes to toff[cur ^ 1]
+struct MsmState;
+__global__ void scan_blocks_gated_kernel(const uint32_t *__restrict__ in, uint32_t *const outs0, uint32_t *const outs1, const uint32_t *st_words,
+                                         uint32_t *__restrict__ block_sums, uint64_t n) {
+    if (st_words[0] <= 1) return;   // MsmState::maxlen
+    uint32_t *out = st_words[1] ? outs0 : outs1;   // cur == 1 -> write toff[0]
+    __shared__ uint32_t sm[32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLK + (uint64_t)threadIdx.x * SCAN_PER;
+    uint32_t v[SCAN_PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) { v[k] = base + k < n ? in[base + k] : 0; sum += v[k]; }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(sum, &total, sm);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void scan_sums_gated_kernel(uint32_t *__restrict__ block_sums, uint32_t nblocks, uint32_t *const outs0, uint32_t *const outs1,
+                                       const uint32_t *st_words, uint64_t n) {
+    if (st_words[0] <= 1) return;
+    uint32_t *out = st_words[1] ? outs0 : outs1;
+    __shared__ uint32_t sm[32];
+    uint32_t running = 0;
+    for (uint32_t s = 0; s < nblocks; s += SCAN_T) {
+        const uint32_t idx = s + threadIdx.x;
+        const uint32_t v = idx < nblocks ? block_sums[idx] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, &total, sm);
+        if (idx < nblocks) block_sums[idx] = running + ex;
+        running += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = running;
+}
+__global__ void scan_add_gated_kernel(uint32_t *const outs0, uint32_t *const outs1, const uint32_t *st_words, const uint32_t *__restrict__ block_sums,
+                                      uint64_t n) {
+    if (st_words[0] <= 1) return;
+    uint32_t *out = st_words[1] ? outs0 : outs1;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLK + (uint64_t)threadIdx.x * SCAN_PER;
+    const uint32_t add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
 // out[0..n) = exclusive scan of in, out[n] = total.  tmp: ceil(n / SCAN_BLK) u32
 static void exclusive_scan_u32(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *tmp, cudaStream_t st) {
     const uint32_t nblocks = (uint32_t)((n + SCAN_BLK - 1) / SCAN_BLK);
@@ -151,30 +200,40 @@ static void exclusive_scan_u32(zkb_ctx *ctx, const uint32_t *in, uint32_t *out, 
     ctx->launches += 3;
 }
 
-// ---- bucket accumulation: balanced tasks of at most ACC_CH entries ---------------------------------------------------
-// Witness columns are highly structured (most scalars are 0, 1 or small), so bucket sizes are wildly skewed: a bucket is
-// cut into ceil(len / ACC_CH) tasks; level 0 adds affine bases gathered through the sorted index list, the following levels
-// add the XYZZ partials of the previous level, until every bucket holds one value.  Task -> bucket by binary search in the
-// exclusive scan of per-bucket task counts.
+// ---- bucket accumulation: equal chunks of the sorted pair list, then levels of <= ACC_CH-entry tasks per bucket -----------
+// Witness columns are highly structured (most scalars are 0, 1 or small), so bucket sizes are wildly skewed, and even for
+// random scalars the lengths inside a warp differ (Poisson): one thread per bucket (or per ceil(len/64) task) leaves ~30 % of
+// the lanes idle.  Level 0 therefore cuts the SORTED PAIR LIST into chunks of exactly CHUNK entries: chunk t adds entries
+// [CHUNK t, CHUNK (t+1)) and flushes a partial whenever it crosses a bucket boundary; bucket b (entries [off_b, off_{b+1}))
+// receives one partial from each chunk it intersects, at slot toff[b] + (t - off_b / CHUNK).  The following levels add the XYZZ
+// partials of a bucket in tasks of <= ACC_CH until every bucket holds one value.  Task -> bucket by binary search in the
+// exclusive scan of the per-bucket task counts.
 constexpr uint32_t ACC_CH = 64;
+constexpr uint32_t CHUNK = 32;
 
-__global__ void task_count_kernel(const uint32_t *__restrict__ seg_off, uint32_t nseg, uint32_t *__restrict__ tcount) {
+// device-side pipeline state: lets the reduction levels run (or exit immediately) without a round trip to the host
+struct MsmState {
+    uint32_t maxlen;      // longest partial list of any bucket after the last executed level
+    uint32_t cur;         // which of the two partial / task-offset arrays holds the current lists
+    uint32_t levels_run;
+    uint32_t pad;
+    uint64_t extra_adds;  // additions performed by levels >= 1
+};
+
+// number of chunks bucket b intersects (0 for an empty bucket) + the maximum over all buckets
+__global__ void chunk_count_kernel(const uint32_t *__restrict__ seg_off, uint32_t nseg, uint32_t *__restrict__ tcount, MsmState *st) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nseg) return;
-    const uint32_t len = seg_off[b + 1] - seg_off[b];
-    tcount[b] = (len + ACC_CH - 1) / ACC_CH;
-}
-__global__ void max_u32_kernel(const uint32_t *__restrict__ off, uint32_t nseg, uint32_t *__restrict__ out) {
-    uint32_t m = 0;
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nseg; b += gridDim.x * blockDim.x) {
-        const uint32_t len = off[b + 1] - off[b];
-        m = len > m ? len : m;
+    uint32_t cnt = 0;
+    if (b < nseg) {
+        const uint32_t lo = seg_off[b], hi = seg_off[b + 1];
+        cnt = hi > lo ? (hi - 1) / CHUNK - lo / CHUNK + 1 : 0;
+        tcount[b] = cnt;
     }
     for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t y = __shfl_down_sync(0xffffffffu, m, o);
-        m = y > m ? y : m;
+        const uint32_t y = __shfl_down_sync(0xffffffffu, cnt, o);
+        cnt = y > cnt ? y : cnt;
     }
-    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+    if ((threadIdx.x & 31) == 0 && cnt > 1) atomicMax(&st->maxlen, cnt);
 }
 __device__ __forceinline__ uint32_t find_segment(const uint32_t *__restrict__ toff, uint32_t nseg, uint32_t t) {
     // largest b with toff[b] <= t   (toff has nseg + 1 entries, non-decreasing)
@@ -185,44 +244,88 @@ __device__ __forceinline__ uint32_t find_segment(const uint32_t *__restrict__ to
     }
     return lo;
 }
-__global__ void __launch_bounds__(128) msm_acc_level0_kernel(const G1Affine *__restrict__ bases, const uint32_t *__restrict__ seg_off,
-                                                            const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ toff,
-                                                            uint32_t nseg, uint32_t ntasks, G1Xyzz *__restrict__ part) {
+__global__ void __launch_bounds__(128) msm_acc_chunk_kernel(const G1Affine *__restrict__ bases, const uint32_t *__restrict__ seg_off,
+                                                           const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ toff,
+                                                           uint32_t nseg, G1Xyzz *__restrict__ part) {
+    const uint32_t total = seg_off[nseg];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntasks) return;
-    const uint32_t b = find_segment(toff, nseg, t);
-    const uint32_t beg = seg_off[b] + (t - toff[b]) * ACC_CH;
-    const uint32_t lim = seg_off[b + 1];
-    const uint32_t end = beg + ACC_CH < lim ? beg + ACC_CH : lim;
+    const uint32_t beg = t * CHUNK;
+    if (beg >= total) return;
+    const uint32_t end = beg + CHUNK < total ? beg + CHUNK : total;
+    uint32_t b = find_segment(seg_off, nseg, beg);   // the (non-empty) bucket holding entry `beg`
+    uint32_t b_first = seg_off[b], next = seg_off[b + 1];
     G1Xyzz acc = G1Xyzz::identity();
+    uint32_t e = sorted[beg];
+    G1Affine p = g1_load_affine(bases + (e & 0x7fffffffu));
     for (uint32_t k = beg; k < end; ++k) {
-        const uint32_t e = sorted[k];
-        G1Affine p = g1_load_affine(bases + (e & 0x7fffffffu));
-        if (e >> 31) p = g1_neg(p);
-        g1_add_mixed(acc, p);
+        if (k == next) {
+            g1_store_xyzz(part + toff[b] + (t - b_first / CHUNK), acc);
+            acc = G1Xyzz::identity();
+            do { ++b; next = seg_off[b + 1]; } while (next <= k);
+            b_first = seg_off[b];
+        }
+        // fetch the next entry's base while this addition runs
+        const uint32_t e_cur = e;
+        const G1Affine p_cur = p;
+        if (k + 1 < end) {
+            e = sorted[k + 1];
+            p = g1_load_affine(bases + (e & 0x7fffffffu));
+        }
+        g1_add_mixed(acc, (e_cur >> 31) ? g1_neg(p_cur) : p_cur);
     }
-    g1_store_xyzz(part + t, acc);
+    g1_store_xyzz(part + toff[b] + (t - b_first / CHUNK), acc);
 }
-__global__ void __launch_bounds__(128) msm_acc_levelN_kernel(const G1Xyzz *__restrict__ in, const uint32_t *__restrict__ seg_off,
-                                                            const uint32_t *__restrict__ toff, uint32_t nseg, uint32_t ntasks,
-                                                            G1Xyzz *__restrict__ part) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntasks) return;
-    const uint32_t b = find_segment(toff, nseg, t);
-    const uint32_t beg = seg_off[b] + (t - toff[b]) * ACC_CH;
-    const uint32_t lim = seg_off[b + 1];
-    const uint32_t end = beg + ACC_CH < lim ? beg + ACC_CH : lim;
-    G1Xyzz acc = g1_load_xyzz(in + beg);
-    for (uint32_t k = beg + 1; k < end; ++k) g1_add(acc, g1_load_xyzz(in + k));
-    g1_store_xyzz(part + t, acc);
-}
-// buckets[b] = the single remaining partial of segment b (or the identity for an empty bucket)
-__global__ void msm_gather_buckets_kernel(const G1Xyzz *__restrict__ part, const uint32_t *__restrict__ seg_off, uint32_t nseg,
-                                          G1Xyzz *__restrict__ buckets) {
+
+// ---- levels >= 1 (all gated on the device-side state: a level that is not needed costs one empty launch per kernel) ----------
+struct LevelBufs {
+    uint32_t *toff[2];      // per-bucket offsets of the partial lists (nseg + 1 entries each)
+    G1Xyzz *part[2];
+    uint32_t *tcount;
+    MsmState *st;
+};
+__global__ void level_task_count_kernel(LevelBufs L, uint32_t nseg) {
+    if (L.st->maxlen <= 1) return;
+    const uint32_t *seg_off = L.toff[L.st->cur];
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nseg) return;
+    const uint32_t len = seg_off[b + 1] - seg_off[b];
+    L.tcount[b] = (len + ACC_CH - 1) / ACC_CH;
+}
+__global__ void __launch_bounds__(128) msm_acc_levelN_kernel(LevelBufs L, uint32_t nseg) {
+    if (L.st->maxlen <= 1) return;
+    const uint32_t cur = L.st->cur;
+    const uint32_t *__restrict__ seg_off = L.toff[cur];
+    const uint32_t *__restrict__ toff = L.toff[cur ^ 1];
+    const G1Xyzz *__restrict__ in = L.part[cur];
+    G1Xyzz *__restrict__ part = L.part[cur ^ 1];
+    const uint32_t ntasks = toff[nseg];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntasks; t += gridDim.x * blockDim.x) {
+        const uint32_t b = find_segment(toff, nseg, t);
+        const uint32_t beg = seg_off[b] + (t - toff[b]) * ACC_CH;
+        const uint32_t lim = seg_off[b + 1];
+        const uint32_t end = beg + ACC_CH < lim ? beg + ACC_CH : lim;
+        G1Xyzz acc = g1_load_xyzz(in + beg);
+        for (uint32_t k = beg + 1; k < end; ++k) g1_add(acc, g1_load_xyzz(in + k));
+        g1_store_xyzz(part + t, acc);
+    }
+}
+__global__ void level_advance_kernel(LevelBufs L, uint32_t nseg) {
+    MsmState *st = L.st;
+    if (st->maxlen <= 1) return;
+    const uint32_t cur = st->cur;
+    st->extra_adds += L.toff[cur][nseg];   // entries consumed by this level (one addition each, minus one per task)
+    st->maxlen = (st->maxlen + ACC_CH - 1) / ACC_CH;
+    st->cur = cur ^ 1;
+    st->levels_run++;
+}
+// buckets[b] = the single remaining partial of segment b (or the identity for an empty bucket)
+__global__ void msm_gather_buckets_kernel(LevelBufs L, uint32_t nseg, G1Xyzz *__restrict__ buckets) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nseg) return;
+    const uint32_t cur = L.st->cur;
+    const uint32_t *seg_off = L.toff[cur];
     const uint32_t beg = seg_off[b], end = seg_off[b + 1];
-    g1_store_xyzz(buckets + b, end > beg ? g1_load_xyzz(part + beg) : G1Xyzz::identity());
+    g1_store_xyzz(buckets + b, end > beg ? g1_load_xyzz(L.part[cur] + beg) : G1Xyzz::identity());
 }
 
 // ---- window reduction: sum_j j * in[j] (0-based weights) by levels of length-L running sums ----------------------------
@@ -377,9 +480,11 @@ int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uin
     const uint32_t nbuckets = batch * rwin1 * m.half;
     const uint64_t pairs = n * windows1 * batch;
     ZKB_ARG(pairs < (1ull << 32) && (uint64_t)batch * rwin1 * m.half < (1ull << 31));
-    const uint32_t log_l = 5;  // window-reduction segment length 32
+    // window-reduction segment length 2^log_l: short segments when a single column would otherwise leave the SMs empty
+    uint32_t log_l = 5;
+    while (log_l > 3 && (uint64_t)batch * rwin1 * (m.half >> log_l) < 32768) --log_l;
 
-    // scratch A: counts | offsets(+1) | cursors | tcount | toffA(+1) | toffB(+1) | scan tmp | max
+    // scratch A: counts | offsets(+1) | cursors | tcount | toffA(+1) | toffB(+1) | scan tmp | state
     const size_t cnt_bytes = align_up((size_t)(nbuckets + 2) * 4, 256);
     const size_t tmp_bytes = align_up(((size_t)nbuckets / SCAN_BLK + 2) * 4, 256);
     uint8_t *A = nullptr, *B = nullptr, *C = nullptr;
@@ -387,67 +492,67 @@ int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uin
     ZKB_TRY(scratch_get(ctx, SCR_MSM_B, pairs * 4, (void **)&B));
     uint32_t *counts = (uint32_t *)A, *offsets = (uint32_t *)(A + cnt_bytes), *cursors = (uint32_t *)(A + 2 * cnt_bytes);
     uint32_t *tcount = (uint32_t *)(A + 3 * cnt_bytes), *toff[2] = {(uint32_t *)(A + 4 * cnt_bytes), (uint32_t *)(A + 5 * cnt_bytes)};
-    uint32_t *scan_tmp = (uint32_t *)(A + 6 * cnt_bytes), *d_max = (uint32_t *)(A + 6 * cnt_bytes + tmp_bytes);
+    uint32_t *scan_tmp = (uint32_t *)(A + 6 * cnt_bytes);
+    MsmState *d_state = (MsmState *)(A + 6 * cnt_bytes + tmp_bytes);
     uint32_t *sorted = (uint32_t *)B;
 
+    // scratch C, sized from BOUNDS (no count returns to the host): level 0 emits at most one partial per chunk plus one per
+    // bucket; every later level at most (previous / ACC_CH + one per bucket)
+    const uint32_t half = m.half;
+    const uint32_t wred = rwin1 * batch;  // reduction windows: from the scatter on a (column, bucket set) pair is just a window
+    uint32_t nlevels = 0, cnt = half;
+    size_t level_entries = 0;
+    while (cnt > 1) { cnt = (cnt + (1u << log_l) - 1) >> log_l; level_entries += 2ull * cnt * wred; nlevels++; }
+    if (nlevels == 0) { nlevels = 1; level_entries = 2ull * wred; }  // half == 1: one trivial level
+    const size_t part0_n = (size_t)((pairs + CHUNK - 1) / CHUNK) + nbuckets + 1;
+    const size_t part1_n = part0_n / ACC_CH + nbuckets + 1;
+    ZKB_ARG(part0_n < (1ull << 32));
+    const size_t c_entries = part0_n + part1_n + nbuckets + level_entries + (size_t)nlevels * wred + 2ull * wred;
+    ZKB_TRY(scratch_get(ctx, SCR_MSM_C, c_entries * sizeof(G1Xyzz), (void **)&C));
+    G1Xyzz *part[2] = {(G1Xyzz *)C, (G1Xyzz *)C + part0_n};
+    G1Xyzz *buckets = part[1] + part1_n, *lvl = buckets + nbuckets, *lvl_sums = lvl + level_entries, *all_sum = lvl_sums + (size_t)nlevels * wred,
+           *wres = all_sum + wred;
+
     ZKB_CUDA(cudaMemsetAsync(counts, 0, cnt_bytes, st));
-    ZKB_CUDA(cudaMemsetAsync(d_max, 0, 4, st));
+    ZKB_CUDA(cudaMemsetAsync(d_state, 0, sizeof(MsmState), st));
     const unsigned tb = 256, bb = (nbuckets + 255) / 256;
     const dim3 gb((unsigned)((n + tb - 1) / tb), batch);
     msm_digits_kernel<0><<<gb, tb, 0, st>>>(d_scalar_cols, n, m, counts, nullptr, nullptr);
     exclusive_scan_u32(ctx, counts, offsets, nbuckets, scan_tmp, st);
     ZKB_CUDA(cudaMemcpyAsync(cursors, offsets, (size_t)nbuckets * 4, cudaMemcpyDeviceToDevice, st));
     msm_digits_kernel<1><<<gb, tb, 0, st>>>(d_scalar_cols, n, m, nullptr, cursors, sorted);
-    m.windows = rwin1 * batch;  // from here on a (column, bucket set) pair is just a window
-    max_u32_kernel<<<64, 256, 0, st>>>(offsets, nbuckets, d_max);
-    task_count_kernel<<<bb, 256, 0, st>>>(offsets, nbuckets, tcount);
+    m.windows = wred;
+    chunk_count_kernel<<<bb, 256, 0, st>>>(offsets, nbuckets, tcount, d_state);
     exclusive_scan_u32(ctx, tcount, toff[0], nbuckets, scan_tmp, st);
-    ctx->launches += 4;
-    uint32_t h_info[2] = {0, 0};  // total pairs, level-0 tasks
-    uint32_t h_max = 0;
-    ZKB_CUDA(cudaMemcpyAsync(&h_info[0], offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st));
-    ZKB_CUDA(cudaMemcpyAsync(&h_info[1], toff[0] + nbuckets, 4, cudaMemcpyDeviceToHost, st));
-    ZKB_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
-    ZKB_CUDA(cudaStreamSynchronize(st));
-    const uint32_t total_pairs = h_info[0];
-    uint32_t ntasks = h_info[1];
-
-    // scratch C: part0 | part1 | buckets | level arrays (acc / run per level) | level sums | all-sum | window results
-    const uint32_t half = m.half;
-    uint32_t nlevels = 0, cnt = half;
-    size_t level_entries = 0;
-    while (cnt > 1) { cnt = (cnt + (1u << log_l) - 1) >> log_l; level_entries += 2ull * cnt * m.windows; nlevels++; }
-    if (nlevels == 0) { nlevels = 1; level_entries = 2ull * m.windows; }  // half == 1: one trivial level
-    const size_t part0_n = ntasks ? ntasks : 1, part1_n = (ntasks + ACC_CH - 1) / ACC_CH + nbuckets + 1;
-    const size_t c_entries = part0_n + part1_n + nbuckets + level_entries + (size_t)nlevels * m.windows + 2ull * m.windows;
-    ZKB_TRY(scratch_get(ctx, SCR_MSM_C, c_entries * sizeof(G1Xyzz), (void **)&C));
-    G1Xyzz *part[2] = {(G1Xyzz *)C, (G1Xyzz *)C + part0_n};
-    G1Xyzz *buckets = part[1] + part1_n, *lvl = buckets + nbuckets, *lvl_sums = lvl + level_entries, *all_sum = lvl_sums + (size_t)nlevels * m.windows,
-           *wres = all_sum + m.windows;
-
-    uint64_t extra_adds = 0;
-    if (ntasks) msm_acc_level0_kernel<<<(ntasks + 127) / 128, 128, 0, st>>>(bases, offsets, sorted, toff[0], nbuckets, ntasks, part[0]);
-    ctx->launches++;
-    // further levels while some bucket still holds more than one partial
-    int cur = 0;
-    uint32_t maxlen = (h_max + ACC_CH - 1) / ACC_CH;  // partials per bucket after level 0
-    const uint32_t *seg_off = toff[0];
-    while (maxlen > 1) {
-        const int nxt = cur ^ 1;
-        task_count_kernel<<<bb, 256, 0, st>>>(seg_off, nbuckets, tcount);
-        exclusive_scan_u32(ctx, tcount, toff[nxt], nbuckets, scan_tmp, st);
-        uint32_t nt = 0;
-        ZKB_CUDA(cudaMemcpyAsync(&nt, toff[nxt] + nbuckets, 4, cudaMemcpyDeviceToHost, st));
-        ZKB_CUDA(cudaStreamSynchronize(st));
-        msm_acc_levelN_kernel<<<(nt + 127) / 128, 128, 0, st>>>(part[cur], seg_off, toff[nxt], nbuckets, nt, part[nxt]);
-        ctx->launches += 2;
-        extra_adds += ntasks;
-        ntasks = nt;
-        seg_off = toff[nxt];
-        cur = nxt;
-        maxlen = (maxlen + ACC_CH - 1) / ACC_CH;
+    // level 0: one thread per 32-entry chunk of the sorted list (grid from the bound; surplus threads exit on the device-side total)
+    {
+        const uint64_t max_chunks = (pairs + CHUNK - 1) / CHUNK;
+        msm_acc_chunk_kernel<<<(unsigned)((max_chunks + 127) / 128), 128, 0, st>>>(bases, offsets, sorted, toff[0], nbuckets, part[0]);
     }
-    msm_gather_buckets_kernel<<<bb, 256, 0, st>>>(part[cur], seg_off, nbuckets, buckets);
+    ctx->launches += 4;
+    // levels >= 1: as many as the longest possible partial list needs; each one exits at once when the lists are already single
+    LevelBufs L;
+    L.toff[0] = toff[0]; L.toff[1] = toff[1];
+    L.part[0] = part[0]; L.part[1] = part[1];
+    L.tcount = tcount;
+    L.st = d_state;
+    {
+        uint64_t bound = (n * (shifted ? windows1 : 1) + CHUNK - 1) / CHUNK + 1;   // partials of the fullest possible bucket
+        const uint32_t nscan = (uint32_t)(((uint64_t)nbuckets + SCAN_BLK - 1) / SCAN_BLK);
+        const uint32_t *stw = (const uint32_t *)d_state;
+        const unsigned lv_blocks = (unsigned)std::min<uint64_t>((part0_n / ACC_CH + nbuckets + 127) / 128, 148ull * 32);
+        while (bound > 1) {
+            level_task_count_kernel<<<bb, 256, 0, st>>>(L, nbuckets);
+            scan_blocks_gated_kernel<<<nscan, SCAN_T, 0, st>>>(tcount, toff[0], toff[1], stw, scan_tmp, nbuckets);
+            scan_sums_gated_kernel<<<1, SCAN_T, 0, st>>>(scan_tmp, nscan, toff[0], toff[1], stw, nbuckets);
+            scan_add_gated_kernel<<<nscan, SCAN_T, 0, st>>>(toff[0], toff[1], stw, scan_tmp, nbuckets);
+            msm_acc_levelN_kernel<<<lv_blocks, 128, 0, st>>>(L, nbuckets);
+            level_advance_kernel<<<1, 1, 0, st>>>(L, nbuckets);
+            ctx->launches += 6;
+            bound = (bound + ACC_CH - 1) / ACC_CH;
+        }
+    }
+    msm_gather_buckets_kernel<<<bb, 256, 0, st>>>(L, nbuckets, buckets);
     ctx->launches++;
 
     // window reduction by levels
@@ -477,8 +582,12 @@ int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uin
     ZKB_CUDA(cudaGetLastError());
 
     std::vector<G1Xyzz> h(m.windows);
+    MsmState h_state;
+    uint32_t total_pairs = 0;
     ZKB_CUDA(cudaMemcpyAsync(h.data(), wres, m.windows * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
-    ZKB_CUDA(cudaStreamSynchronize(st));
+    ZKB_CUDA(cudaMemcpyAsync(&h_state, d_state, sizeof(MsmState), cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaMemcpyAsync(&total_pairs, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaStreamSynchronize(st));   // the ONLY synchronisation of an MSM: its result is needed on the host (transcript)
     // Horner over windows on the host (W * c doublings + W additions of single points), per column
     for (uint32_t col = 0; col < batch; ++col) {
         const G1Xyzz *hw = h.data() + (size_t)col * rwin1;
@@ -489,7 +598,8 @@ int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uin
         }
         out_affine_host[col] = g1_to_affine(acc);
     }
-    ctx->msm_last_adds = (uint64_t)total_pairs + extra_adds + 2ull * nbuckets;
+    ctx->msm_last_adds = (uint64_t)total_pairs + h_state.extra_adds + 2ull * nbuckets;
+    ctx->msm_last_levels = h_state.levels_run;
     return ZKB_OK;
 }
 

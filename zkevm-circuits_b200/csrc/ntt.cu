@@ -1,105 +1,138 @@
-// ntt.cu -- radix-2 NTT over BN254 Fr for sm_100a.
+// ntt.cu -- radix-2 NTT over BN254 Fr for sm_100a: persistent CTAs, TMA-staged data and twiddle tiles, mbarrier pipeline.
 //
 // Replaces halo2_proofs::arithmetic::best_fft (halo2_proofs 1.1.0 @ e5ddf67 src/arithmetic.rs; reached from
 // circuit-benchmarks/src/super_circuit.rs:117-132 through EvaluationDomain::{lagrange_to_coeff, coeff_to_extended,
 // extended_to_coeff}).  Same contract: in place, natural order in / natural order out, a'[k] = sum_j a[j] w^(jk).
 //
 // B200 design (NOT upstream's bit-reverse + log n global layers):
-//   n = A1 * A2 (* A3), every factor <= 2^12.  Pass p runs all length-A_p transforms of the Cooley-Tukey index
-//   splitting j = j_a * inner + j_in entirely inside one CTA's shared memory (A_p * 32 B <= 128 KB, split into two
-//   16-byte planes so 128-bit LDS/STS are conflict free), decimation-in-frequency, and applies the inter-pass
-//   twiddle w_n^(j_in * k_a) on the way out.  A 2^24 transform is two passes = two reads + two writes of the data,
-//   the minimum for a working set larger than shared memory.  Each 32-byte element is exactly one DRAM sector, so
-//   the strided column gathers of pass 1 and the digit-reversed scatter of the last pass move no wasted bytes.
-//   Twiddles: a 2^(a-1)-entry local table per pass (L1/L2 resident) + a two-level table (w^lo * w^(hi*4096)) for
-//   the inter-pass factor.  The 1/n of the inverse transform is folded into the two-level table (no extra multiply).
-//   The kernels are bound by the integer-multiply pipe: 1 Montgomery multiply (264 IMAD) per butterfly.
+//   n = A1 * A2 (* A3), every factor <= 2^11 (1 pass up to 2^11, 2 passes up to 2^22, 3 passes above).  A pass is ONE
+//   persistent kernel (one CTA per SM) that walks over TILES of 2048 elements (64 KB): a tile is C = 2048 / A adjacent
+//   columns of the Cooley-Tukey index split, i.e. C independent length-A transforms whose rows are C*32 contiguous bytes in
+//   HBM.  Per tile:
+//     * the data tile is fetched by TMA (cp.async.bulk.tensor.2d through a per-column tensor map: box = 256 rows x 32 B;
+//       the contiguous tiles of the last pass by cp.async.bulk) into one of TWO shared-memory buffers, one tile AHEAD of
+//       the arithmetic, completion signalled on an mbarrier (complete_tx::bytes);
+//     * the tile's inter-pass twiddles w_n^(j_in * k) are a TMA-staged tile as well: the table is stored tile-major in the
+//       order the tile consumes it, so one 64 KB cp.async.bulk brings them in while the butterflies run;
+//     * the A/2 local twiddles of the pass sit in shared memory for the life of the CTA (one bulk copy at kernel start);
+//     * decimation in frequency in radix-8 rounds held in registers (8 elements / thread / round, 256 threads, no spills),
+//       two 16-byte planes with an XOR swizzle + one padding slot per column -> conflict-free 128-bit LDS/STS;
+//     * results leave through 32-byte streaming stores, C adjacent threads writing C*32 contiguous bytes.
+//   The multiplier pipe (1 Montgomery multiply = 139 IMAD.WIDE per butterfly) is the bound, not HBM: the TMA pipeline keeps
+//   it fed during what used to be the load and store phases of a single resident CTA.
+//   Scaling by 1/n (any caller scale) is folded into the last inter-pass table; zeta-coset scaling and an arbitrary
+//   per-element input scale are fused into the first / last register round.
 #include "common.cuh"
+#include <string.h>
+#include <algorithm>
+#include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
 
 namespace zkb {
 
-constexpr int NTT_MAX_BITS = 12;  // largest in-CTA transform: 4096 elements = 128 KB of shared memory
+constexpr int NTT_TILE_BITS = 11;   // 2048 elements = 64 KB per tile
+constexpr int NTT_MAX_BITS = 11;    // largest in-CTA transform
+constexpr int NTT_THREADS = 256;    // 8 elements per thread and round
 constexpr int TW_LO_BITS = 12;
+constexpr uint32_t NTT_BOX_ROWS = 256;
+constexpr uint32_t NTT_HDR_BYTES = 128;                                  // mbarriers
+constexpr uint32_t NTT_DBUF_BYTES = 32u * ((1u << NTT_TILE_BITS) + 32u);  // two 16-byte planes of C*(A+1) <= 2048+32 slots
+constexpr uint32_t NTT_TWBUF_BYTES = 32u << NTT_TILE_BITS;
 
 // ZETA = 7^((r-1)/3) and ZETA^2 (Montgomery form); EvaluationDomain::g_coset / g_coset_inv (poly/domain.rs)
 __device__ __constant__ uint32_t ZETA_POW[2][8];
 
 struct PassArgs {
-    uint32_t a;          // log2 of the in-CTA transform length
-    uint32_t log_inner;  // log2 of the element stride inside this pass
+    uint32_t a;          // log2 of the in-CTA transform length A
+    uint32_t log_c;      // log2 of the number of columns per tile (C * A = tile elements)
+    uint32_t log_inner;  // log2 of the element stride S between the rows of this pass
     uint32_t log_n;
-    uint32_t tw_shift;   // boundary exponent = (j_in * k) << tw_shift
-    uint32_t is_final;   // inner == 1: digit-reversed store
-    uint32_t a1, a2;     // bits of the earlier passes (final store index = k1 + (k2 << a1) + (k << (a1 + a2)))
+    uint32_t is_final;   // last pass: contiguous sub-transforms in, digit-reversed scatter out
+    uint32_t a1, a2;     // final pass: bits of the first / middle pass (oidx = k1 + (k2 << a1) + (k << (a1 + a2)))
     uint32_t coset_in;   // multiply input i by ZETA^(i mod 3)        (first pass only)
     uint32_t coset_out;  // multiply output k by ZETA^(-(k mod 3))    (final pass only)
     uint32_t use_scale;  // multiply outputs by *scale                 (single-pass transforms only)
-    const Fr *loc;
-    const Fr *tw_lo;
-    const Fr *tw_hi;
+    uint32_t has_in_scale;
+    uint32_t tiles_per_col, total_tiles;
+    const Fr *loc;       // 2^(a-1) local twiddles of this pass
+    const Fr *tw;        // inter-pass table of this boundary, tile-major (non-final passes)
     const Fr *scale;
     const Fr *in_scale;  // optional per-element input multiplier (first pass only): coset scaling tables
-    // batching over blockIdx.y: column y reads in_tbl[y] (or in + y * in_stride) and writes out_tbl[y] (or out + y * out_stride)
-    const Fr *tw_full;   // optional complete inter-pass table (first pass of a two-pass plan)
-    const Fr *const *in_tbl;
-    Fr *const *out_tbl;
-    uint64_t in_stride, out_stride;
+    const CUtensorMap *maps;   // per column: 2-D view [n / S rows][S * 4 u64] of the pass input (non-final passes)
+    const Fr *const *src;      // per column input  (final pass: bulk copies)
+    Fr *const *dst;            // per column output
 };
 
-// element i lives at slot i ^ ((i >> 3) & 7): keeps unit-stride runs conflict free AND makes the stride-8 accesses of the
-// last radix-8 round (a thread owns 8 consecutive elements) hit 8 distinct 16-byte bank groups
+struct TileInfo {
+    uint32_t y;       // column of the batch
+    uint32_t c0;      // first column of the tile (non-final: j_in block; final: k1 block)
+    uint32_t outer;   // non-final: index of the enclosing outer block; final: k2
+    uint32_t tw_tile;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const PassArgs &p, uint32_t gt) {
+    TileInfo t;
+    t.y = gt / p.tiles_per_col;
+    const uint32_t tau = gt - t.y * p.tiles_per_col;
+    const uint32_t lb = (p.is_final ? p.a1 : p.log_inner) - p.log_c;  // log2 (number of column blocks)
+    const uint32_t blk = tau & ((1u << lb) - 1);
+    t.outer = tau >> lb;
+    t.c0 = blk << p.log_c;
+    t.tw_tile = blk;
+    return t;
+}
+
+// ---- PTX wrappers: mbarrier + TMA -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "NTT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra NTT_DONE;\n"
+        "bra NTT_WAIT;\n"
+        "NTT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int32_t x, int32_t y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- shared-memory element access -----------------------------------------------------------------------------------------
+// L0: the layout TMA leaves: element (c, r) at byte (c * A + r) * 32.
+// L1: two 16-byte planes, element (c, r) at slot c * (A + 1) + (r ^ ((r >> 3) & 7)): unit-stride runs stay conflict free, the
+//     stride-8 pattern of the last radix-8 round hits 8 distinct bank groups, and the +1 per column spreads the columns of a
+//     row over distinct banks for the store phase.
 __device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u); }
-__device__ __forceinline__ Fr smem_ld(const uint4 *lo, const uint4 *hi, uint32_t i) {
-    const uint32_t k = swz(i);
-    uint4 a = lo[k], b = hi[k];
+__device__ __forceinline__ Fr ld_pair(const uint4 *lo, const uint4 *hi) {
+    const uint4 a = *lo, b = *hi;
     Fr r;
     r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
-__device__ __forceinline__ void smem_st(uint4 *lo, uint4 *hi, uint32_t i, const Fr &v) {
-    const uint32_t k = swz(i);
-    lo[k] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-    hi[k] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+__device__ __forceinline__ Fr ld_lin(const uint8_t *buf, uint32_t idx) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(buf) + 2 * (size_t)idx;
+    return ld_pair(q, q + 1);
 }
-// R consecutive DIF stages (s .. s+R-1) on groups of 2^R elements held in registers: one shared-memory round trip and
-// one barrier per R stages; the 2^R - 1 distinct twiddles of a group are loaded once.
-template <int R>
-__device__ __forceinline__ void ntt_round(uint4 *lo, uint4 *hi, uint32_t a, uint32_t s, const Fr *__restrict__ loc, uint32_t tid, uint32_t nt) {
-    constexpr int E = 1 << R;
-    const uint32_t A = 1u << a;
-    const uint32_t h = A >> (s + 1);
-    const uint32_t q = h >> (R - 1);          // spacing of the group's elements = half distance of the round's last stage
-    const uint32_t lq = 31 - __clz(q);
-    for (uint32_t g = tid; g < (A >> R); g += nt) {
-        const uint32_t p_local = g & (q - 1);
-        const uint32_t base = ((g >> lq) << (lq + R)) + p_local;
-        Fr x[E];
-#pragma unroll
-        for (int m = 0; m < E; ++m) x[m] = smem_ld(lo, hi, base + ((uint32_t)m << lq));
-#pragma unroll
-        for (int t = 0; t < R; ++t) {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int d = E >> (t + 1);
-            const bool last_trivial = ((uint32_t)d << lq) == 1u;   // half distance 1: twiddle is omega^0
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-                if ((m & d) == 0) {
-                    const Fr u = x[m], v = x[m + d];
-                    x[m] = fp_add(u, v);
-                    Fr dif = fp_sub(u, v);
-                    if (!last_trivial) {
-                        const uint32_t pos = p_local + ((uint32_t)(m & (d - 1)) << lq);
-                        dif = fp_mul(dif, fp_load(loc + ((size_t)pos << (s + t))));
-                    }
-                    x[m + d] = dif;
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < E; ++m) smem_st(lo, hi, base + ((uint32_t)m << lq), x[m]);
-    }
+__device__ __forceinline__ Fr ld_l1(const uint4 *lo, const uint4 *hi, uint32_t slot) { return ld_pair(lo + slot, hi + slot); }
+__device__ __forceinline__ void st_l1(uint4 *lo, uint4 *hi, uint32_t slot, const Fr &v) {
+    lo[slot] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[slot] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 __device__ __forceinline__ Fr zeta_pow(int i) {  // i in {1,2}
     Fr z;
@@ -108,112 +141,216 @@ __device__ __forceinline__ Fr zeta_pow(int i) {  // i in {1,2}
     return z;
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(const Fr *__restrict__ in_base, Fr *__restrict__ out_base, PassArgs p) {
-    extern __shared__ uint4 smem[];
-    const Fr *__restrict__ in = p.in_tbl ? p.in_tbl[blockIdx.y] : in_base + (size_t)blockIdx.y * p.in_stride;
-    Fr *__restrict__ out = p.out_tbl ? p.out_tbl[blockIdx.y] : out_base + (size_t)blockIdx.y * p.out_stride;
-    const uint32_t A = 1u << p.a;
-    uint4 *lo = smem, *hi = smem + A;
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    const uint64_t sub = blockIdx.x;
-    const uint64_t outer = sub >> p.log_inner;
-    const uint64_t j_in = sub & ((1ull << p.log_inner) - 1);
-    const uint64_t base = (outer << (p.a + p.log_inner)) + j_in;
-
-    // load phase: 4 independent 32-byte loads in flight per thread before anything is consumed
-    for (uint32_t j0 = tid; j0 < A; j0 += 4 * nt) {
-        Fr v[4];
-        uint64_t idx[4];
+// R consecutive DIF stages (s .. s+R-1) on groups of 2^R elements held in registers: one shared-memory round trip and one
+// barrier per R stages.  Every thread owns 8 element slots per round (8 / 2^R groups).  FIRST: the inputs are read from the
+// TMA layout L0 (with the fused input scalings), then -- after a barrier, the conversion is in place -- written in L1.
+template <int R, bool FIRST>
+__device__ __forceinline__ void ntt_round(uint8_t *dbuf, const PassArgs &p, const TileInfo &ti, uint32_t s, const uint8_t *loc_sm, uint32_t tid) {
+    constexpr int E = 1 << R, NG = 8 / E;
+    const uint32_t a = p.a, A = 1u << a;
+    const uint32_t elems = 1u << (a + p.log_c);
+    const uint32_t total_groups = elems >> R;
+    const uint32_t lgpc = a - R;           // log2 (groups per column)
+    const uint32_t lq = a - s - R;         // log2 of the spacing of a group's elements (half distance of the round's last stage)
+    const uint32_t q = 1u << lq;
+    uint4 *lo = reinterpret_cast<uint4 *>(dbuf);
+    uint4 *hi = lo + ((A + 1) << p.log_c);
+    Fr x[8];
+    uint32_t cbase[NG], rbase[NG], ploc[NG];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t j = j0 + u * nt;
-            idx[u] = base + ((uint64_t)j << p.log_inner);
-            if (j < A) v[u] = fp_load_stream(in + idx[u]);
+    for (int u = 0; u < NG; ++u) {
+        // a tile shorter than 8 x 256 elements (single-pass transforms below 2^11) wraps: the surplus threads redo a valid
+        // group and write identical values, which keeps the register arrays free of divergent definitions
+        const uint32_t G = (tid + u * NTT_THREADS) & (total_groups - 1);
+        const uint32_t c = G >> lgpc, g = G & ((1u << lgpc) - 1);
+        ploc[u] = g & (q - 1);
+        rbase[u] = ((g >> lq) << (lq + R)) + ploc[u];
+        cbase[u] = c;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const uint32_t r = rbase[u] + ((uint32_t)m << lq);
+            if (FIRST) x[u * E + m] = ld_lin(dbuf, (c << a) + r);
+            else x[u * E + m] = ld_l1(lo, hi, c * (A + 1) + swz(r));
         }
+    }
+    if (FIRST) {
+        if (p.coset_in || p.has_in_scale) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t j = j0 + u * nt;
-            if (j < A) {
-                if (p.coset_in) {
-                    const uint32_t m = (uint32_t)(idx[u] % 3);
-                    if (m) v[u] = fp_mul(v[u], zeta_pow(m));
+            for (int u = 0; u < NG; ++u) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const uint32_t r = rbase[u] + ((uint32_t)m << lq);
+                    const uint32_t idx = (r << p.log_inner) + ti.c0 + cbase[u];   // first pass: outer == 0
+                    if (p.coset_in) {
+                        const uint32_t z = idx % 3;
+                        if (z) x[u * E + m] = fp_mul(x[u * E + m], zeta_pow(z));
+                    }
+                    if (p.has_in_scale) x[u * E + m] = fp_mul(x[u * E + m], fp_load(p.in_scale + idx));
                 }
-                if (p.in_scale) v[u] = fp_mul(v[u], fp_load(p.in_scale + idx[u]));
-                smem_st(lo, hi, j, v[u]);
             }
         }
+        __syncthreads();  // every L0 read is done before the first L1 write (same bytes)
+    }
+#pragma unroll
+    for (int u = 0; u < NG; ++u) {
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const int d = E >> (t + 1);
+            const bool last_trivial = ((uint32_t)d << lq) == 1u;   // half distance 1: twiddle is omega^0
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                if ((m & d) == 0) {
+                    const Fr uu = x[u * E + m], vv = x[u * E + m + d];
+                    x[u * E + m] = fp_add(uu, vv);
+                    Fr dif = fp_sub(uu, vv);
+                    if (!last_trivial) {
+                        const uint32_t pos = ploc[u] + ((uint32_t)(m & (d - 1)) << lq);
+                        dif = fp_mul(dif, ld_lin(loc_sm, pos << (s + t)));
+                    }
+                    x[u * E + m + d] = dif;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const uint32_t r = rbase[u] + ((uint32_t)m << lq);
+            st_l1(lo, hi, cbase[u] * (A + 1) + swz(r), x[u * E + m]);
+        }
+    }
+}
+
+// thread 0: start the TMA traffic of one tile into data buffer `dst` (shared address), completion on `bar`
+__device__ __forceinline__ void issue_data(const PassArgs &p, uint32_t gt, uint32_t dst, uint32_t bar) {
+    const TileInfo t = decode_tile(p, gt);
+    const uint32_t A = 1u << p.a, C = 1u << p.log_c;
+    mbar_expect_tx(bar, (A << p.log_c) * 32u);
+    if (!p.is_final) {
+        const CUtensorMap *map = p.maps + t.y;
+        const uint32_t br = A < NTT_BOX_ROWS ? A : NTT_BOX_ROWS;
+        for (uint32_t c = 0; c < C; ++c)
+            for (uint32_t r0 = 0; r0 < A; r0 += br)
+                tma_load_2d(dst + ((c << p.a) + r0) * 32u, map, (int32_t)((t.c0 + c) * 4u), (int32_t)((t.outer << p.a) + r0), bar);
+    } else {
+        const Fr *src = p.src[t.y];
+        for (uint32_t c = 0; c < C; ++c) {
+            const uint64_t sub = ((uint64_t)(t.c0 + c) << p.a2) + t.outer;   // sub-transform (k1, k2): input is contiguous
+            tma_load_bulk(dst + (c << p.a) * 32u, src + (sub << p.a), A * 32u, bar);
+        }
+    }
+}
+__device__ __forceinline__ void issue_tw(const PassArgs &p, uint32_t gt, uint32_t dst, uint32_t bar) {
+    const TileInfo t = decode_tile(p, gt);
+    const uint32_t bytes = 32u << (p.a + p.log_c);
+    mbar_expect_tx(bar, bytes);
+    tma_load_bulk(dst, p.tw + ((size_t)t.tw_tile << (p.a + p.log_c)), bytes, bar);
+}
+
+__global__ void __launch_bounds__(NTT_THREADS, 1) ntt_tile_kernel(const __grid_constant__ PassArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t a = p.a, A = 1u << a, C = 1u << p.log_c, elems = A << p.log_c;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // [0],[1] data buffers, [2] twiddle tile, [3] local twiddles
+    uint8_t *twbuf = smem + NTT_HDR_BYTES + 2 * NTT_DBUF_BYTES;
+    uint8_t *locbuf = twbuf + (p.is_final ? 0u : NTT_TWBUF_BYTES);
+    const uint32_t bar_d[2] = {smem_u32(bars), smem_u32(bars + 1)};
+    const uint32_t bar_tw = smem_u32(bars + 2), bar_loc = smem_u32(bars + 3);
+    const uint32_t stride = gridDim.x;
+    uint32_t gt = blockIdx.x;
+    if (gt >= p.total_tiles) return;
+
+    if (tid == 0) {
+        mbar_init(bar_d[0], 1); mbar_init(bar_d[1], 1); mbar_init(bar_tw, 1); mbar_init(bar_loc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-
-    // decimation in frequency: natural order in, bit-reversed order out (inside shared memory); radix-8 rounds in registers
-    {
-        uint32_t s = 0;
-        while (p.a - s >= 3) { ntt_round<3>(lo, hi, p.a, s, p.loc, tid, nt); __syncthreads(); s += 3; }
-        if (p.a - s == 2) { ntt_round<2>(lo, hi, p.a, s, p.loc, tid, nt); __syncthreads(); }
-        else if (p.a - s == 1) { ntt_round<1>(lo, hi, p.a, s, p.loc, tid, nt); __syncthreads(); }
+    if (tid == 0) {
+        const uint32_t loc_bytes = (a ? (A >> 1) : 1u) * 32u;
+        mbar_expect_tx(bar_loc, loc_bytes);
+        tma_load_bulk(smem_u32(locbuf), p.loc, loc_bytes, bar_loc);
+        issue_data(p, gt, smem_u32(smem + NTT_HDR_BYTES), bar_d[0]);
+        if (!p.is_final) issue_tw(p, gt, smem_u32(twbuf), bar_tw);
     }
+    mbar_wait(bar_loc, 0);
 
-    if (p.is_final) {
-        const uint64_t k1 = p.a2 ? (outer >> p.a2) : outer;
-        const uint64_t k2 = p.a2 ? (outer & ((1ull << p.a2) - 1)) : 0;
-        const uint64_t obase = (p.a1 ? k1 : 0) + (k2 << p.a1);
-        for (uint32_t q = tid; q < A; q += nt) {
-            const uint32_t k = p.a ? (__brev(q) >> (32 - p.a)) : 0;
-            Fr v = smem_ld(lo, hi, q);
-            const uint64_t oidx = obase + ((uint64_t)k << (p.a1 + p.a2));
-            if (p.use_scale) v = fp_mul(v, fp_load(p.scale));
-            if (p.coset_out) {
-                const uint32_t m = (uint32_t)(oidx % 3);
-                if (m) v = fp_mul(v, zeta_pow(3 - m));  // ZETA^(-m) = ZETA^(3-m)
-            }
-            fp_store_stream(out + oidx, v);
+    for (uint32_t it = 0; gt < p.total_tiles; ++it, gt += stride) {
+        const uint32_t b = it & 1;
+        // the other buffer was released by the barrier that closed the previous iteration: fetch the next tile into it now
+        if (tid == 0 && gt + stride < p.total_tiles) issue_data(p, gt + stride, smem_u32(smem + NTT_HDR_BYTES + (b ^ 1) * NTT_DBUF_BYTES), bar_d[b ^ 1]);
+        const TileInfo ti = decode_tile(p, gt);
+        uint8_t *d = smem + NTT_HDR_BYTES + b * NTT_DBUF_BYTES;
+        mbar_wait(bar_d[b], (it >> 1) & 1);
+
+        // decimation in frequency: natural order in, bit-reversed order out (inside shared memory); radix-8 rounds in registers
+        // (transforms shorter than 8 points first convert the TMA layout with the degenerate round<0>)
+        {
+            uint32_t s = 0;
+            if (a >= 3) { ntt_round<3, true>(d, p, ti, 0, locbuf, tid); s = 3; }
+            else ntt_round<0, true>(d, p, ti, 0, locbuf, tid);
+            __syncthreads();
+            while (a - s >= 3) { ntt_round<3, false>(d, p, ti, s, locbuf, tid); __syncthreads(); s += 3; }
+            if (a - s == 2) { ntt_round<2, false>(d, p, ti, s, locbuf, tid); __syncthreads(); }
+            else if (a - s == 1) { ntt_round<1, false>(d, p, ti, s, locbuf, tid); __syncthreads(); }
         }
-    } else {
-        // inter-pass twiddle w_n^(j_in * k) = lo[e & 4095] * hi[e >> 12]: the table reads of two elements are issued together
-        const bool two_level = p.log_n > TW_LO_BITS;
-        for (uint32_t q0 = tid; q0 < A; q0 += 2 * nt) {
-            uint32_t k[2];
-            Fr tl[2], th[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const uint32_t q = q0 + u * nt;
-                k[u] = __brev(q) >> (32 - p.a);
-                if (q < A) {
-                    if (p.tw_full) tl[u] = fp_load_stream(p.tw_full + (j_in << p.a) + k[u]);
-                    else {
-                        const uint64_t e = (j_in * (uint64_t)k[u]) << p.tw_shift;
-                        tl[u] = fp_load(p.tw_lo + (e & ((1u << TW_LO_BITS) - 1)));
-                        if (two_level) th[u] = fp_load(p.tw_hi + (e >> TW_LO_BITS));
+
+        const uint4 *lo = reinterpret_cast<const uint4 *>(d);
+        const uint4 *hi = lo + ((A + 1) << p.log_c);
+        Fr *__restrict__ out = p.dst[ti.y];
+        if (!p.is_final) {
+            mbar_wait(bar_tw, it & 1);
+            // slot q of a column holds output k = bitrev(q); the staged table is [q][c] in exactly this order
+#pragma unroll 4
+            for (uint32_t u = 0; u < 8; ++u) {
+                const uint32_t e = tid + u * NTT_THREADS;
+                if (e < elems) {
+                    const uint32_t c = e & (C - 1), q = e >> p.log_c;
+                    const uint32_t k = __brev(q) >> (32 - a);   // a >= 1 in non-final passes
+                    const Fr v = fp_mul(ld_l1(lo, hi, c * (A + 1) + swz(q)), ld_lin(twbuf, e));
+                    const uint64_t oidx = ((((uint64_t)ti.outer << a) + k) << p.log_inner) + ti.c0 + c;
+                    fp_store_stream(out + oidx, v);
+                }
+            }
+        } else {
+            const uint64_t obase = (uint64_t)ti.c0 + ((uint64_t)ti.outer << p.a1);
+#pragma unroll 4
+            for (uint32_t u = 0; u < 8; ++u) {
+                const uint32_t e = tid + u * NTT_THREADS;
+                if (e < elems) {
+                    const uint32_t c = e & (C - 1), q = e >> p.log_c;
+                    const uint32_t k = a ? (__brev(q) >> (32 - a)) : 0;
+                    Fr v = ld_l1(lo, hi, c * (A + 1) + swz(q));
+                    const uint64_t oidx = obase + c + ((uint64_t)k << (p.a1 + p.a2));
+                    if (p.use_scale) v = fp_mul(v, fp_load(p.scale));
+                    if (p.coset_out) {
+                        const uint32_t m = (uint32_t)(oidx % 3);
+                        if (m) v = fp_mul(v, zeta_pow(3 - m));  // ZETA^(-m) = ZETA^(3-m)
                     }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const uint32_t q = q0 + u * nt;
-                if (q < A) {
-                    Fr tw = (two_level && !p.tw_full) ? fp_mul(tl[u], th[u]) : tl[u];
-                    const Fr v = fp_mul(smem_ld(lo, hi, q), tw);
-                    fp_store_stream(out + base + ((uint64_t)k[u] << p.log_inner), v);
+                    fp_store_stream(out + oidx, v);
                 }
             }
         }
+        // generic-proxy accesses of this tile's buffers are ordered before the async-proxy (TMA) writes that reuse them
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0 && !p.is_final && gt + stride < p.total_tiles) issue_tw(p, gt + stride, smem_u32(twbuf), bar_tw);
     }
 }
 
-// T[j_in * A + k] = lo[e & 4095] * hi[e >> 12], e = j_in * k  (lo may carry a folded scale)
-__global__ void build_full_table_kernel(const Fr *__restrict__ lo, const Fr *__restrict__ hi, uint32_t log_n, uint32_t a0, Fr *__restrict__ out) {
+// Boundary table of a non-final pass, tile-major: entry [cblk][q][c] = w_n^((j_in * bitrev_a(q)) << shift) (x scale),
+// j_in = cblk * C + c, built from the two-level table lo[e & 4095] * hi[e >> 12].
+__global__ void build_boundary_table_kernel(const Fr *__restrict__ lo, const Fr *__restrict__ hi, uint32_t log_n, uint32_t a, uint32_t log_c,
+                                            uint32_t log_inner, uint32_t shift, const Fr *__restrict__ scale, Fr *__restrict__ out) {
     const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (idx >= (1ull << log_n)) return;
-    const uint64_t j_in = idx >> a0, k = idx & ((1ull << a0) - 1);
-    const uint64_t e = j_in * k;
+    if (idx >= (1ull << (a + log_inner))) return;
+    const uint32_t c = (uint32_t)(idx & ((1u << log_c) - 1));
+    const uint32_t q = (uint32_t)((idx >> log_c) & ((1u << a) - 1));
+    const uint64_t cblk = idx >> (log_c + a);
+    const uint64_t j_in = (cblk << log_c) + c;
+    const uint64_t k = a ? (__brev(q) >> (32 - a)) : 0;
+    const uint64_t e = (j_in * k) << shift;
     Fr tw = fp_load(lo + (e & ((1u << TW_LO_BITS) - 1)));
     if (log_n > TW_LO_BITS) tw = fp_mul(tw, fp_load(hi + (e >> TW_LO_BITS)));
+    if (scale) tw = fp_mul(tw, fp_load(scale));
     fp_store(out + idx, tw);
-}
-
-__global__ void scale_table_kernel(const Fr *__restrict__ in, Fr *__restrict__ out, const Fr *__restrict__ scale, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) fp_store(out + i, fp_mul(fp_load(in + i), fp_load(scale)));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -245,7 +382,20 @@ static int32_t upload_powers(zkb_ctx *ctx, const Fr &w, size_t count, Fr **out) 
     return ZKB_OK;
 }
 
-static bool g_zeta_uploaded[64] = {false};
+// per-pass geometry shared by the plan builder and the launcher
+struct PassGeom { uint32_t a, log_inner, log_c, shift; bool is_final; };
+static void pass_geometry(const NttPlan &plan, int ps, PassGeom &g) {
+    uint32_t consumed = 0;
+    for (int q = 0; q < ps; ++q) consumed += plan.bits[q];
+    g.a = plan.bits[ps];
+    g.shift = consumed;
+    g.log_inner = plan.log_n - consumed - g.a;
+    g.is_final = (ps == plan.npass - 1);
+    uint32_t lc = NTT_TILE_BITS - g.a;                     // C * A = 2048 ...
+    const uint32_t cap = g.is_final ? (plan.npass > 1 ? (uint32_t)plan.bits[0] : 0u) : g.log_inner;  // ... unless fewer columns exist
+    if (lc > cap) lc = cap;
+    g.log_c = lc;
+}
 
 static int32_t get_plan(zkb_ctx *ctx, uint32_t log_n, const Fr &omega, NttPlan **out) {
     std::array<uint64_t, 5> key;
@@ -253,14 +403,6 @@ static int32_t get_plan(zkb_ctx *ctx, uint32_t log_n, const Fr &omega, NttPlan *
     for (int i = 0; i < 4; ++i) key[1 + i] = (uint64_t)omega.l[2 * i] | ((uint64_t)omega.l[2 * i + 1] << 32);
     auto it = ctx->ntt_plans.find(key);
     if (it != ctx->ntt_plans.end()) { *out = &it->second; return ZKB_OK; }
-
-    if (!g_zeta_uploaded[ctx->device & 63]) {
-        Fr z = host_zeta(), z2 = fp_sqr(z);
-        uint32_t h[2][8];
-        for (int i = 0; i < 8; ++i) { h[0][i] = z.l[i]; h[1][i] = z2.l[i]; }
-        ZKB_CUDA(cudaMemcpyToSymbol(ZETA_POW, h, sizeof(h)));
-        g_zeta_uploaded[ctx->device & 63] = true;
-    }
 
     // order check: omega^(2^log_n) == 1 and omega^(2^(log_n-1)) == -1
     {
@@ -290,111 +432,156 @@ static int32_t get_plan(zkb_ctx *ctx, uint32_t log_n, const Fr &omega, NttPlan *
         for (uint32_t i = a; i < log_n; ++i) w = fp_sqr(w);  // omega^(2^(log_n - a)) : order 2^a
         ZKB_TRY(upload_powers(ctx, w, a ? ((size_t)1 << (a - 1)) : 1, &plan.loc[ps]));
     }
+    // unscaled boundary tables (n entries for the first boundary, A2 * A3 for the second)
+    for (int ps = 0; ps + 1 < plan.npass; ++ps) {
+        PassGeom g;
+        pass_geometry(plan, ps, g);
+        const uint64_t entries = 1ull << (g.a + g.log_inner);
+        ZKB_CUDA(cudaMalloc((void **)&plan.tw_b[ps], entries * sizeof(Fr)));
+        build_boundary_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, ctx->stream>>>(plan.tw_lo, plan.tw_hi, log_n, g.a, g.log_c, g.log_inner,
+                                                                                              g.shift, nullptr, plan.tw_b[ps]);
+        ctx->launches++;
+    }
+    ZKB_CUDA(cudaGetLastError());
     auto ins = ctx->ntt_plans.emplace(key, plan);
     *out = &ins.first->second;
     return ZKB_OK;
 }
 
-static bool g_attr_set = false;
+// ---- tensor maps ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// 2-D view of one column for a pass with row stride S = 2^log_inner elements: dim0 = S * 4 u64 (one row of S elements), dim1 = n / S rows;
+// box = one element (4 u64 = 32 B) x min(A, 256) rows
+static int32_t encode_column_map(CUtensorMap *m, const Fr *base, uint32_t log_n, uint32_t log_inner, uint32_t a) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ZKB_ERR_CUDA; }
+    const cuuint64_t dims[2] = {(cuuint64_t)4 << log_inner, (cuuint64_t)1 << (log_n - log_inner)};
+    const cuuint64_t strides[1] = {(cuuint64_t)32 << log_inner};
+    const uint32_t A = 1u << a;
+    const cuuint32_t box[2] = {4, A < NTT_BOX_ROWS ? A : NTT_BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for log_n %u log_inner %u a %u", (int)r, log_n, log_inner, a); return ZKB_ERR_CUDA; }
+    return ZKB_OK;
+}
 
-// batch of `count` transforms: column y reads d_src_tbl[y], writes d_dst_tbl[y] (device pointer tables; tables may alias).
-// With count == 1 and null tables, src/dst are used directly.
-int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, const Fr *const *d_src_tbl, Fr *const *d_dst_tbl, uint32_t count,
-                            uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, cudaStream_t st) {
-    ZKB_ARG(log_n <= 3 * NTT_MAX_BITS && log_n <= 28 && count >= 1);
+static uint32_t pass_smem_bytes(const PassGeom &g) {
+    return NTT_HDR_BYTES + 2 * NTT_DBUF_BYTES + (g.is_final ? 0u : NTT_TWBUF_BYTES) + (g.a ? (32u << (g.a - 1)) : 32u);
+}
+
+// batch of `count` transforms: column y reads h_src[y], writes h_dst[y] (HOST arrays of device pointers; the arrays may alias,
+// h_src[y] == h_dst[y] is an in-place transform).
+int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_dst, uint32_t count, uint32_t log_n, const Fr &omega,
+                            const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, cudaStream_t st) {
+    ZKB_ARG(log_n <= 3 * NTT_MAX_BITS && log_n <= 28 && count >= 1 && h_src && h_dst);
     ZKB_ARG(coset_zeta >= 0 && coset_zeta <= 2);
     NttPlan *plan = nullptr;
     ZKB_TRY(get_plan(ctx, log_n, omega, &plan));
-    if (!g_attr_set) {
-        ZKB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_MAX_BITS) * 32));
-        g_attr_set = true;
+    if (!ctx->ntt_ready) {
+        // per device (a context owns one device): opt in to the large dynamic shared-memory window, upload ZETA
+        ZKB_CUDA(cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        Fr z = host_zeta(), z2 = fp_sqr(z);
+        uint32_t h[2][8];
+        for (int i = 0; i < 8; ++i) { h[0][i] = z.l[i]; h[1][i] = z2.l[i]; }
+        ZKB_CUDA(cudaMemcpyToSymbol(ZETA_POW, h, sizeof(h)));
+        ctx->ntt_ready = true;
     }
     const uint64_t n = 1ull << log_n;
+    const int npass = plan->npass;
     Fr *scratch = nullptr;
-    if (plan->npass > 1) ZKB_TRY(scratch_get(ctx, SCR_NTT, (size_t)count * n * sizeof(Fr), (void **)&scratch));
+    if (npass > 1) ZKB_TRY(scratch_get(ctx, SCR_NTT, (size_t)count * n * sizeof(Fr), (void **)&scratch));
 
-    // scale: folded into the two-level twiddle table for multi-pass transforms
+    // scale: single pass -> multiplied at the store; otherwise folded into the last boundary table (cached per scale value)
     Fr *d_scale = nullptr;
-    const Fr *tw_lo = plan->tw_lo;
+    const Fr *last_tw = npass > 1 ? plan->tw_b[npass - 2] : nullptr;
     if (scale_host) {
         void *misc = nullptr;
-        ZKB_TRY(scratch_get(ctx, SCR_MISC, ((size_t)1 << TW_LO_BITS) * sizeof(Fr) + sizeof(Fr), &misc));
+        ZKB_TRY(scratch_get(ctx, SCR_MISC, sizeof(Fr), &misc));
         d_scale = (Fr *)misc;
-        ZKB_CUDA(cudaMemcpyAsync(d_scale, scale_host, sizeof(Fr), cudaMemcpyHostToDevice, st));
-        if (plan->npass > 1) {
-            Fr *scaled = d_scale + 1;
-            const uint32_t cnt = 1u << TW_LO_BITS;
-            scale_table_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(plan->tw_lo, scaled, d_scale, cnt);
-            ctx->launches++;
-            tw_lo = scaled;
-        }
-    }
-
-    // complete inter-pass table for two-pass plans (built once per plan / scale, n multiplies)
-    const Fr *tw_full = nullptr;
-    if (plan->npass == 2 && log_n <= 25) {
-        const unsigned bb = (unsigned)((n + 255) / 256);
-        if (!scale_host) {
-            if (!plan->tw_full) {
-                ZKB_CUDA(cudaMalloc((void **)&plan->tw_full, n * sizeof(Fr)));
-                build_full_table_kernel<<<bb, 256, 0, st>>>(plan->tw_lo, plan->tw_hi, log_n, plan->bits[0], plan->tw_full);
-                ctx->launches++;
-            }
-            tw_full = plan->tw_full;
+        if (npass == 1) {
+            ZKB_CUDA(cudaMemcpyAsync(d_scale, scale_host, sizeof(Fr), cudaMemcpyHostToDevice, st));
         } else {
-            if (!plan->tw_full_scaled) ZKB_CUDA(cudaMalloc((void **)&plan->tw_full_scaled, n * sizeof(Fr)));
+            PassGeom g;
+            pass_geometry(*plan, npass - 2, g);
+            const uint64_t entries = 1ull << (g.a + g.log_inner);
+            if (!plan->tw_b_scaled) ZKB_CUDA(cudaMalloc((void **)&plan->tw_b_scaled, entries * sizeof(Fr)));
             if (!plan->has_scaled || !(plan->scaled_key == *scale_host)) {
-                build_full_table_kernel<<<bb, 256, 0, st>>>(tw_lo, plan->tw_hi, log_n, plan->bits[0], plan->tw_full_scaled);  // tw_lo = scaled copy
+                ZKB_CUDA(cudaMemcpyAsync(d_scale, scale_host, sizeof(Fr), cudaMemcpyHostToDevice, st));
+                build_boundary_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(plan->tw_lo, plan->tw_hi, log_n, g.a, g.log_c, g.log_inner,
+                                                                                              g.shift, d_scale, plan->tw_b_scaled);
                 ctx->launches++;
                 plan->scaled_key = *scale_host;
                 plan->has_scaled = true;
             }
-            tw_full = plan->tw_full_scaled;
+            last_tw = plan->tw_b_scaled;
         }
     }
 
-    uint32_t log_inner = log_n;
-    for (int ps = 0; ps < plan->npass; ++ps) {
-        const uint32_t a = plan->bits[ps];
-        log_inner -= a;
-        PassArgs p;
-        p.a = a;
-        p.log_inner = log_inner;
-        p.log_n = log_n;
-        p.is_final = (ps == plan->npass - 1);
-        uint32_t consumed = 0;
-        for (int q = 0; q <= ps; ++q) consumed += plan->bits[q];
-        p.tw_shift = consumed - a;  // bits consumed by the earlier passes
-        p.a1 = p.a2 = 0;
-        if (p.is_final) {
-            if (plan->npass == 2) { p.a1 = plan->bits[0]; }
-            if (plan->npass == 3) { p.a1 = plan->bits[0]; p.a2 = plan->bits[1]; }
+    // descriptor blob: per non-final pass `count` tensor maps, then per pass the src / dst pointer tables
+    const size_t maps_bytes = (size_t)(npass - 1) * count * sizeof(CUtensorMap);
+    const size_t tbl_bytes = (size_t)count * sizeof(void *);
+    const size_t blob_bytes = maps_bytes + 2 * (size_t)npass * tbl_bytes;
+    std::vector<uint8_t> blob(blob_bytes + 64);
+    uint8_t *hb = blob.data();
+    uint8_t *hb_al = hb + ((64 - ((uintptr_t)hb & 63)) & 63);   // CUtensorMap wants 64-byte alignment (also on the host side)
+    uint8_t *dblob = nullptr;
+    ZKB_TRY(scratch_get(ctx, SCR_NTT_DESC, blob_bytes + 64, (void **)&dblob));
+    for (int ps = 0; ps < npass; ++ps) {
+        PassGeom g;
+        pass_geometry(*plan, ps, g);
+        const Fr **srcs = (const Fr **)(hb_al + maps_bytes + (size_t)(2 * ps) * tbl_bytes);
+        Fr **dsts = (Fr **)(hb_al + maps_bytes + (size_t)(2 * ps + 1) * tbl_bytes);
+        for (uint32_t y = 0; y < count; ++y) {
+            srcs[y] = ps == 0 ? h_src[y] : scratch + (size_t)y * n;
+            dsts[y] = g.is_final ? h_dst[y] : scratch + (size_t)y * n;
+            ZKB_ARG(srcs[y] != nullptr && dsts[y] != nullptr);
+            if (!g.is_final) ZKB_TRY(encode_column_map((CUtensorMap *)(hb_al + ((size_t)ps * count + y) * sizeof(CUtensorMap)), srcs[y], log_n, g.log_inner, g.a));
         }
+    }
+    ZKB_CUDA(cudaMemcpyAsync(dblob, hb_al, blob_bytes, cudaMemcpyHostToDevice, st));
+
+    for (int ps = 0; ps < npass; ++ps) {
+        PassGeom g;
+        pass_geometry(*plan, ps, g);
+        PassArgs p;
+        memset(&p, 0, sizeof(p));
+        p.a = g.a;
+        p.log_c = g.log_c;
+        p.log_inner = g.log_inner;
+        p.log_n = log_n;
+        p.is_final = g.is_final;
+        if (g.is_final && npass == 2) { p.a1 = plan->bits[0]; }
+        if (g.is_final && npass == 3) { p.a1 = plan->bits[0]; p.a2 = plan->bits[1]; }
         p.coset_in = (ps == 0 && coset_zeta == 1);
-        p.coset_out = (p.is_final && coset_zeta == 2);
-        p.use_scale = (plan->npass == 1 && scale_host != nullptr);
+        p.coset_out = (g.is_final && coset_zeta == 2);
+        p.use_scale = (npass == 1 && scale_host != nullptr);
+        p.has_in_scale = (ps == 0 && d_in_scale != nullptr);
+        p.tiles_per_col = (uint32_t)(n >> (g.a + g.log_c));
+        p.total_tiles = p.tiles_per_col * count;
         p.loc = plan->loc[ps];
-        p.tw_lo = (ps == 0) ? tw_lo : plan->tw_lo;  // only the first boundary carries the folded scale
-        p.tw_hi = plan->tw_hi;
+        p.tw = g.is_final ? nullptr : (ps == npass - 2 ? last_tw : plan->tw_b[ps]);
         p.scale = d_scale;
-        p.in_scale = (ps == 0) ? d_in_scale : nullptr;
-        p.tw_full = (ps == 0) ? tw_full : nullptr;
-        p.in_tbl = nullptr;
-        p.out_tbl = nullptr;
-        p.in_stride = p.out_stride = 0;
-        const Fr *src = nullptr;
-        Fr *dst = nullptr;
-        const bool first = (ps == 0), last = p.is_final;
-        if (first) { if (d_src_tbl) p.in_tbl = d_src_tbl; else src = src_data; }
-        else { src = scratch; p.in_stride = n; }
-        if (last) { if (d_dst_tbl) p.out_tbl = d_dst_tbl; else dst = data; }
-        else { dst = scratch; p.out_stride = n; }
-        const uint32_t A = 1u << a;
-        uint32_t threads = A / 8;  // one radix-8 group per thread and round
-        if (threads < 64) threads = 64;
-        if (threads > 512) threads = 512;
-        const uint64_t blocks = n >> a;
-        ntt_pass_kernel<<<dim3((unsigned)blocks, count), threads, (size_t)A * 32, st>>>(src, dst, p);
+        p.in_scale = d_in_scale;
+        p.maps = (const CUtensorMap *)(dblob + (size_t)ps * count * sizeof(CUtensorMap));
+        p.src = (const Fr *const *)(dblob + maps_bytes + (size_t)(2 * ps) * tbl_bytes);
+        p.dst = (Fr *const *)(dblob + maps_bytes + (size_t)(2 * ps + 1) * tbl_bytes);
+        ZKB_ARG((uint64_t)p.tiles_per_col * count < (1ull << 32));
+        const uint32_t grid = p.total_tiles < (uint32_t)ctx->sm_count ? p.total_tiles : (uint32_t)ctx->sm_count;
+        ntt_tile_kernel<<<grid, NTT_THREADS, pass_smem_bytes(g), st>>>(p);
         ctx->launches++;
     }
     ZKB_CUDA(cudaGetLastError());
@@ -403,7 +590,7 @@ int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, const Fr
 
 int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src_data, Fr *data, uint32_t log_n, const Fr &omega, const Fr *scale_host, int coset_zeta,
                       const Fr *d_in_scale, cudaStream_t st) {
-    return ntt_fr_batch_device(ctx, src_data, data, nullptr, nullptr, 1, log_n, omega, scale_host, coset_zeta, d_in_scale, st);
+    return ntt_fr_batch_device(ctx, &src_data, &data, 1, log_n, omega, scale_host, coset_zeta, d_in_scale, st);
 }
 
 }  // namespace zkb
@@ -429,6 +616,26 @@ extern "C" int32_t zkb_ntt_fr_dev(zkb_ctx *ctx, uint64_t *data_dev, uint32_t log
     memcpy(w.l, omega, 32);
     if (scale) memcpy(sc.l, scale, 32);
     return ntt_fr_device(ctx, (const Fr *)data_dev, (Fr *)data_dev, log_n, w, scale ? &sc : nullptr, coset_zeta, nullptr, pick_stream(ctx, stream));
+}
+
+// `count` in-place transforms of the same size in ONE launch per pass (cols_dev: HOST array of device pointers)
+extern "C" int32_t zkb_ntt_fr_batch_dev(zkb_ctx *ctx, uint64_t *const *cols_dev, uint32_t count, uint32_t log_n, const uint64_t omega[4],
+                                        const uint64_t *scale, int32_t coset_zeta, void *stream) {
+    ZKB_ARG(ctx && cols_dev && omega && count >= 1);
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+    Fr w, sc;
+    memcpy(w.l, omega, 32);
+    if (scale) memcpy(sc.l, scale, 32);
+    cudaStream_t st = pick_stream(ctx, stream);
+    // bound the scratch of multi-pass plans to ~2 GiB per launch group
+    const uint64_t per = (uint64_t)32 << log_n;
+    uint32_t group = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, (1ull << 31) / per));
+    for (uint32_t done = 0; done < count; done += group) {
+        const uint32_t cur = count - done < group ? count - done : group;
+        ZKB_TRY(ntt_fr_batch_device(ctx, (const Fr *const *)(cols_dev + done), (Fr *const *)(cols_dev + done), cur, log_n, w, scale ? &sc : nullptr, coset_zeta,
+                                    nullptr, st));
+    }
+    return ZKB_OK;
 }
 
 extern "C" int32_t zkb_ntt_fr_host(zkb_ctx *ctx, uint64_t *data_host, uint32_t log_n, const uint64_t omega[4], const uint64_t *scale,

@@ -73,7 +73,8 @@ static bool parse_csf(const uint32_t *w, uint64_t nw, Csf &c) {
         if (!need(2)) { set_error("CSF: truncated lookups"); return false; }
         const uint32_t nsets = w[p], width = w[p + 1];
         p += 2;
-        if (!need((uint64_t)(nsets + 1) * width)) { set_error("CSF: truncated lookup body"); return false; }
+        if (nsets == 0 || width == 0 || nsets > 4096 || width > 4096) { set_error("CSF: lookup %u has an implausible shape (%u input sets x %u)", l, nsets, width); return false; }
+        if (!need(((uint64_t)nsets + 1) * (uint64_t)width)) { set_error("CSF: truncated lookup body"); return false; }
         c.lookups[l].inputs.resize(nsets);
         for (uint32_t s = 0; s < nsets; ++s) { c.lookups[l].inputs[s].assign(w + p, w + p + width); p += width; }
         c.lookups[l].table.assign(w + p, w + p + width); p += width;
@@ -166,23 +167,6 @@ static bool fr_less(const Fr &a, const Fr &b) {  // halo2curves Ord: canonical i
 }
 static Fr fr_pow_i64(const Fr &base, const Fr &base_inv, int64_t e) { return e >= 0 ? fp_pow_u64(base, (uint64_t)e) : fp_pow_u64(base_inv, (uint64_t)(-e)); }
 
-struct DevPool {  // owns device allocations of a pk / session; blocks are recycled through the context's block cache
-    zkb_ctx *ctx = nullptr;
-    std::vector<std::pair<void *, size_t>> ptrs;
-    ~DevPool() {
-        if (!ctx) return;
-        cudaStreamSynchronize(ctx->stream);
-        for (auto &p : ptrs) block_free(ctx, p.first, p.second);
-    }
-    int32_t alloc(size_t bytes, void **out) {
-        size_t got = 0;
-        ZKB_TRY(block_alloc(ctx, bytes ? bytes : 32, out, &got));
-        ptrs.push_back({*out, got});
-        return ZKB_OK;
-    }
-    int32_t fr(uint64_t n, Fr **out) { return alloc(n * sizeof(Fr), (void **)out); }
-};
-
 }  // namespace zkb
 using namespace zkb;
 
@@ -196,12 +180,17 @@ struct zkb_pk {
     DevPool pool;
     std::vector<Fr *> fixed_values, fixed_polys, sigma_values, sigma_polys;
     Fr *l0_poly = nullptr, *llast_poly = nullptr, *lblind_poly = nullptr, *xid_poly = nullptr, *omega_pows = nullptr;
-    G1Affine *g = nullptr, *g_lagrange = nullptr;
+    zkb_srs *srs = nullptr;       // shared ParamsKZG handle (owned when the pk was made by the legacy zkb_pk_create)
+    bool owns_srs = false;
+    G1Affine *g = nullptr, *g_lagrange = nullptr;   // = srs->g / srs->g_lagrange
     // coset evaluations of the proof-independent polynomials (fixed, sigma, l_0, l_last, l_blind, X) for every coset part,
     // like upstream's pk.fixed_cosets / permutation cosets / l0 / l_last / l_active_row: [part][poly] -> n elements
     std::vector<std::vector<Fr *>> coset_cache;
-    // window-shifted copies of the SRS (copy w = 2^(c w) * P_i) for the Pippenger variant with one bucket set per column
+    // window-shifted copies of the SRS (copy w = 2^(c w) * P_i) for the Pippenger variant with one bucket set per column (= srs->*_shift)
     G1Affine *g_shift = nullptr, *g_lagrange_shift = nullptr;
+    ~zkb_pk() {
+        if (owns_srs && srs) zkb_srs_destroy(srs);
+    }
 };
 
 struct zkb_session {
@@ -416,17 +405,22 @@ static uint32_t compress_exprs(const Csf &cs, const std::vector<uint32_t> &exprs
 }  // namespace zkb
 
 // ================================================================================================ C ABI: proving key
-extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
-                                 const uint64_t *const *sigma_values, const uint64_t *g, const uint64_t *g_lagrange, zkb_pk **out) {
-    ZKB_ARG(ctx && csf && g && g_lagrange && out);
+// Builds the device-resident proving key.  sigma columns come either from the host (sigma_values) or are already on the
+// device (sigma_dev, keygen path).  The SRS handle is shared, not copied.
+static int32_t pk_build(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values, const uint64_t *const *sigma_values,
+                        const std::vector<Fr *> *sigma_dev, zkb_srs *srs, bool owns_srs, zkb_pk **out) {
+    ZKB_ARG(ctx && csf && srs && out);
     ZKB_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<zkb_pk> pk(new zkb_pk());
     pk->ctx = ctx;
     pk->pool.ctx = ctx;
+    pk->srs = srs;
+    pk->owns_srs = owns_srs;
     ZKB_TRY(zkb_csf_validate(csf, csf_words));
     if (!parse_csf(csf, csf_words, pk->cs)) return ZKB_ERR_ARG;
     const Csf &cs = pk->cs;
-    ZKB_ARG((cs.nf == 0 || fixed_values) && (cs.perm.empty() || sigma_values));
+    ZKB_ARG((cs.nf == 0 || fixed_values) && (cs.perm.empty() || sigma_values || sigma_dev));
+    if (srs->ctx != ctx || srs->k != cs.k) { set_error("the SRS handle is for k = %u on another context or size (circuit k = %u): downsize it first", srs->k, cs.k); return ZKB_ERR_ARG; }
     cudaStream_t st = ctx->stream;
     pk->k = cs.k;
     pk->n = 1ull << cs.k;
@@ -453,23 +447,10 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
         Fr gj = fp_mul(pk->zeta, fp_pow_u64(pk->ext_omega, j));
         pk->t_inv[j] = fp_inv(fp_sub(fp_pow_u64(gj, n), Fr::one()));
     }
-    // SRS
-    ZKB_TRY(pk->pool.alloc(n * sizeof(G1Affine), (void **)&pk->g));
-    ZKB_TRY(pk->pool.alloc(n * sizeof(G1Affine), (void **)&pk->g_lagrange));
-    ZKB_CUDA(cudaMemcpyAsync(pk->g, g, n * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
-    ZKB_CUDA(cudaMemcpyAsync(pk->g_lagrange, g_lagrange, n * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
-    {
-        // window-shifted SRS copies unless they would exceed ZKB_MSM_SHIFT_GB (default 24) in total
-        const uint32_t copies = msm_shift_copies(n);
-        const char *env = getenv("ZKB_MSM_SHIFT_GB");
-        const double budget = (env ? atof(env) : 24.0) * 1e9;
-        if (copies && 2.0 * copies * n * sizeof(G1Affine) <= budget) {
-            ZKB_TRY(pk->pool.alloc((size_t)copies * n * sizeof(G1Affine), (void **)&pk->g_shift));
-            ZKB_TRY(pk->pool.alloc((size_t)copies * n * sizeof(G1Affine), (void **)&pk->g_lagrange_shift));
-            ZKB_TRY(msm_build_shifted_bases(ctx, pk->g, n, pk->g_shift, st));
-            ZKB_TRY(msm_build_shifted_bases(ctx, pk->g_lagrange, n, pk->g_lagrange_shift, st));
-        }
-    }
+    pk->g = srs->g;
+    pk->g_lagrange = srs->g_lagrange;
+    pk->g_shift = srs->g_shift;
+    pk->g_lagrange_shift = srs->g_lagrange_shift;
     // fixed / sigma columns: values and coefficient form
     auto ingest = [&](const uint64_t *const *src, size_t cnt, std::vector<Fr *> &vals, std::vector<Fr *> &polys) -> int32_t {
         vals.resize(cnt);
@@ -483,7 +464,19 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
         return ZKB_OK;
     };
     ZKB_TRY(ingest(fixed_values, cs.nf, pk->fixed_values, pk->fixed_polys));
-    ZKB_TRY(ingest(sigma_values, cs.perm.size(), pk->sigma_values, pk->sigma_polys));
+    if (sigma_dev) {
+        ZKB_ARG(sigma_dev->size() == cs.perm.size());
+        pk->sigma_values.resize(cs.perm.size());
+        pk->sigma_polys.resize(cs.perm.size());
+        for (size_t i = 0; i < cs.perm.size(); ++i) {
+            ZKB_TRY(pk->pool.fr(n, &pk->sigma_values[i]));
+            ZKB_TRY(pk->pool.fr(n, &pk->sigma_polys[i]));
+            ZKB_CUDA(cudaMemcpyAsync(pk->sigma_values[i], (*sigma_dev)[i], n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            ZKB_TRY(lagrange_to_coeff(pk.get(), pk->sigma_values[i], pk->sigma_polys[i], st));
+        }
+    } else {
+        ZKB_TRY(ingest(sigma_values, cs.perm.size(), pk->sigma_values, pk->sigma_polys));
+    }
     // l_0, l_last, l_blind (Lagrange indicator vectors -> coefficient form), X (identity polynomial), omega^i
     ZKB_TRY(pk->pool.fr(n, &pk->l0_poly));
     ZKB_TRY(pk->pool.fr(n, &pk->llast_poly));
@@ -529,6 +522,98 @@ extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf
     }
     ZKB_CUDA(cudaStreamSynchronize(st));
     *out = pk.release();
+    return ZKB_OK;
+}
+
+extern "C" int32_t zkb_pk_create(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
+                                 const uint64_t *const *sigma_values, const uint64_t *g, const uint64_t *g_lagrange, zkb_pk **out) {
+    ZKB_ARG(ctx && csf && csf_words >= 18 && g && g_lagrange && out);
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+    ZKB_TRY(zkb_csf_validate(csf, csf_words));
+    zkb_srs *srs = nullptr;
+    ZKB_TRY(srs_create(ctx, csf[1], (const G1Affine *)g, false, (const G1Affine *)g_lagrange, false, &srs));
+    const int32_t r = pk_build(ctx, csf, csf_words, fixed_values, sigma_values, nullptr, srs, true, out);
+    if (r != ZKB_OK) zkb_srs_destroy(srs);
+    return r;
+}
+extern "C" int32_t zkb_pk_create_with_srs(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values,
+                                          const uint64_t *const *sigma_values, zkb_srs *srs, zkb_pk **out) {
+    return pk_build(ctx, csf, csf_words, fixed_values, sigma_values, nullptr, srs, false, out);
+}
+
+// ---- keygen: permutation assembly + sigma columns (plonk/permutation/keygen.rs Assembly::copy, build_pk) -------------------
+// sigma_i[j] = DELTA^(mapping column) * omega^(mapping row): the cycle structure is merged on the host exactly like upstream
+// (mapping / aux / sizes with union by size -- inherently sequential), the n x P field values are produced on the device.
+__global__ void sigma_from_mapping_kernel(const uint32_t *__restrict__ map_col, const uint32_t *__restrict__ map_row, const Fr *__restrict__ omega_pows,
+                                          const Fr *__restrict__ delta_pows, uint64_t n, Fr *__restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) fp_store(out + i, fp_mul(fp_load(delta_pows + map_col[i]), fp_load(omega_pows + map_row[i])));
+}
+
+// copies: n_copies x 4 u32 = (left column, left row, right column, right row); columns are indices into the CSF's permutation column list
+extern "C" int32_t zkb_keygen_pk(zkb_ctx *ctx, const uint32_t *csf, uint64_t csf_words, const uint64_t *const *fixed_values, const uint32_t *copies,
+                                 uint64_t n_copies, zkb_srs *srs, zkb_pk **out) {
+    ZKB_ARG(ctx && csf && srs && out && (copies || n_copies == 0));
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+    ZKB_TRY(zkb_csf_validate(csf, csf_words));
+    Csf cs;
+    if (!parse_csf(csf, csf_words, cs)) return ZKB_ERR_ARG;
+    const uint64_t n = 1ull << cs.k;
+    const size_t P = cs.perm.size();
+    ZKB_ARG(P * n < (1ull << 32));
+    // Assembly: mapping[c][r] = next cell of the cycle, aux = cycle representative, sizes = cycle length at the representative
+    std::vector<uint32_t> map_col(P * n), map_row(P * n), aux_col(P * n), aux_row(P * n), sizes(P * n, 1);
+    for (size_t c = 0; c < P; ++c)
+        for (uint64_t r = 0; r < n; ++r) { map_col[c * n + r] = aux_col[c * n + r] = (uint32_t)c; map_row[c * n + r] = aux_row[c * n + r] = (uint32_t)r; }
+    for (uint64_t i = 0; i < n_copies; ++i) {
+        const uint32_t lc = copies[4 * i], lr = copies[4 * i + 1], rc = copies[4 * i + 2], rr = copies[4 * i + 3];
+        if (lc >= P || rc >= P || lr >= n || rr >= n) { set_error("copy constraint %llu is out of range", (unsigned long long)i); return ZKB_ERR_ARG; }
+        const size_t a = lc * n + lr, b = rc * n + rr;
+        size_t lcy = aux_col[a] * n + aux_row[a], rcy = aux_col[b] * n + aux_row[b];
+        if (lcy == rcy) continue;
+        if (sizes[lcy] < sizes[rcy]) std::swap(lcy, rcy);
+        sizes[lcy] += sizes[rcy];
+        size_t cur = rcy;
+        do {   // relabel the smaller cycle
+            aux_col[cur] = (uint32_t)(lcy / n);
+            aux_row[cur] = (uint32_t)(lcy % n);
+            cur = map_col[cur] * n + map_row[cur];
+        } while (cur != rcy);
+        std::swap(map_col[a], map_col[b]);
+        std::swap(map_row[a], map_row[b]);
+    }
+    cudaStream_t st = ctx->stream;
+    DevPool tmp;
+    tmp.ctx = ctx;
+    uint32_t *d_mc = nullptr, *d_mr = nullptr;
+    Fr *d_om = nullptr, *d_dl = nullptr;
+    ZKB_TRY(tmp.alloc(P * n * 4 + 4, (void **)&d_mc));
+    ZKB_TRY(tmp.alloc(P * n * 4 + 4, (void **)&d_mr));
+    ZKB_TRY(tmp.fr(n, &d_om));
+    ZKB_TRY(tmp.fr(P + 1, &d_dl));
+    ZKB_CUDA(cudaMemcpyAsync(d_mc, map_col.data(), P * n * 4, cudaMemcpyHostToDevice, st));
+    ZKB_CUDA(cudaMemcpyAsync(d_mr, map_row.data(), P * n * 4, cudaMemcpyHostToDevice, st));
+    Fr omega = host_root_of_unity(cs.k);
+    ZKB_TRY(fr_powers_device(ctx, omega, n, d_om, st));
+    Fr delta = fr_from_u64(7);
+    for (int i = 0; i < 28; ++i) delta = fp_sqr(delta);   // DELTA = 7^(2^28)
+    ZKB_TRY(fr_powers_device(ctx, delta, P + 1, d_dl, st));
+    std::vector<Fr *> sig(P);
+    for (size_t c = 0; c < P; ++c) {
+        ZKB_TRY(tmp.fr(n, &sig[c]));
+        sigma_from_mapping_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_mc + c * n, d_mr + c * n, d_om, d_dl, n, sig[c]);
+        ctx->launches++;
+    }
+    ZKB_CUDA(cudaGetLastError());
+    ZKB_CUDA(cudaStreamSynchronize(st));   // host vectors die at return
+    return pk_build(ctx, csf, csf_words, fixed_values, nullptr, &sig, srs, false, out);
+}
+// sigma column values of a proving key (n x 32 B each, Lagrange basis) back to the host: lets a caller persist / inspect keygen output
+extern "C" int32_t zkb_pk_sigma_read(zkb_pk *pk, uint32_t column, uint64_t *out_host) {
+    ZKB_ARG(pk && out_host && column < pk->sigma_values.size());
+    ZKB_CUDA(cudaSetDevice(pk->ctx->device));
+    ZKB_CUDA(cudaMemcpyAsync(out_host, pk->sigma_values[column], pk->n * sizeof(Fr), cudaMemcpyDeviceToHost, pk->ctx->stream));
+    ZKB_CUDA(cudaStreamSynchronize(pk->ctx->stream));
     return ZKB_OK;
 }
 
@@ -671,6 +756,22 @@ extern "C" int32_t zkb_csf_validate(const uint32_t *csf, uint64_t csf_words) {
         const uint32_t lim = pc[0] == N_FIXED ? c.nf : pc[0] == N_ADVICE ? c.na : pc[0] == N_INSTANCE ? c.ni : 0;
         if (pc[1] >= lim) { set_error("CSF: permutation column out of range"); return ZKB_ERR_ARG; }
     }
+    // queries: column in range, rotation representable in the interpreter's 16-bit field (also for expression nodes)
+    auto chkq = [&](const std::vector<std::array<int32_t, 2>> &q, uint32_t lim, const char *what) {
+        for (auto &e : q) {
+            if (e[0] < 0 || (uint32_t)e[0] >= lim) { set_error("CSF: %s query references column %d of %u", what, e[0], lim); return false; }
+            if (e[1] < -32767 || e[1] > 32767) { set_error("CSF: %s query rotation %d does not fit 16 bits", what, e[1]); return false; }
+        }
+        return true;
+    };
+    if (!chkq(c.advq, c.na, "advice") || !chkq(c.fixq, c.nf, "fixed") || !chkq(c.instq, c.ni, "instance")) return ZKB_ERR_ARG;
+    for (auto &nd : c.nodes) {
+        if (nd[0] == N_FIXED || nd[0] == N_ADVICE || nd[0] == N_INSTANCE) {
+            const int32_t rot = (int32_t)nd[2];
+            if (rot < -32767 || rot > 32767) { set_error("CSF: node rotation %d does not fit 16 bits", rot); return ZKB_ERR_ARG; }
+        }
+    }
+    if ((uint64_t)c.nf + c.na + c.ni + c.perm.size() + 1 >= 65536) { set_error("CSF: more than 65535 column slots"); return ZKB_ERR_ARG; }
     for (uint32_t ph : c.adv_phase) if (ph >= c.nphases) { set_error("CSF: advice phase out of range"); return ZKB_ERR_ARG; }
     for (uint32_t ph : c.ch_phase) if (ph >= c.nphases) { set_error("CSF: challenge phase out of range"); return ZKB_ERR_ARG; }
     return ZKB_OK;
@@ -758,7 +859,12 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
     if (dealt) ZKB_CUDA(cudaMemsetAsync(slab, 0, ncols * n * sizeof(Fr), pk->ctx->copy_stream));
     const uint32_t maxb = msm_max_batch(n);
     const size_t nbatch = dealt ? 1 : (ncols + maxb - 1) / maxb;
-    std::vector<cudaEvent_t> evs(nbatch);
+    struct EventList {   // destroyed on every exit path
+        std::vector<cudaEvent_t> v;
+        ~EventList() { for (auto e : v) if (e) cudaEventDestroy(e); }
+    } evl;
+    evl.v.assign(nbatch, nullptr);
+    std::vector<cudaEvent_t> &evs = evl.v;
     for (size_t b = 0; b < nbatch; ++b) {
         ZKB_CUDA(cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming));
         const size_t lo = dealt ? 0 : b * maxb, hi = dealt ? ncols : std::min(ncols, (b + 1) * (size_t)maxb);
@@ -775,7 +881,6 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
         ZKB_TRY(commit_many(pk, part, pk->g_lagrange, n, cms, st));   // dealt: column i of the phase -> rank i mod P
         for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
     }
-    for (auto &e : evs) cudaEventDestroy(e);
     if (dealt) ZKB_TRY(comm_allreduce_u64(pk->ctx, slab, ncols * n * 4, st));
     for (uint32_t i = 0; i < cs.nch; ++i) {
         if (cs.ch_phase[i] == phase) {
@@ -1074,10 +1179,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         for (size_t done = 0; done < src.size(); done += ntt_chunk) {
             const uint32_t cur = (uint32_t)std::min<size_t>(ntt_chunk, src.size() - done);
             std::vector<Fr *> a(src.begin() + done, src.begin() + done + cur), b(dst.begin() + done, dst.begin() + done + cur);
-            Fr **d_a = nullptr, **d_b = nullptr;
-            ZKB_TRY(upload_table(pool, a, &d_a, st));
-            ZKB_TRY(upload_table(pool, b, &d_b, st));
-            ZKB_TRY(ntt_fr_batch_device(ctx, nullptr, nullptr, d_a, d_b, cur, k, w, scale, 0, in_scale, st));
+            ZKB_TRY(ntt_fr_batch_device(ctx, a.data(), b.data(), cur, k, w, scale, 0, in_scale, st));
         }
         return ZKB_OK;
     };
@@ -1507,15 +1609,21 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
 
 extern "C" int32_t zkb_prove_finish(zkb_session *s, const uint64_t *z_blinds, const uint64_t *phi_blinds, const uint64_t *random_poly,
                                     uint8_t *proof_out, uint64_t proof_cap, uint64_t *proof_len) {
-    ZKB_ARG(s && random_poly && proof_len);
+    ZKB_ARG(s && proof_len);
     zkb_pk *pk = s->pk;
-    if (s->next_phase != pk->cs.nphases || s->finished) { set_error("zkb_prove_finish: advice phases incomplete or session already finished"); return ZKB_ERR_STATE; }
-    ZKB_ARG((pk->nsets == 0 || z_blinds) && (pk->cs.lookups.empty() || phi_blinds));
-    ZKB_CUDA(cudaSetDevice(pk->ctx->device));
-    ZKB_TRY(prove_finish_impl(s, z_blinds, phi_blinds, random_poly));
+    if (!s->finished) {
+        // first call: run the proof.  The bytes stay in the session, so a query call (proof_out == NULL) or a call with a short
+        // buffer loses nothing: call again with a buffer of *proof_len bytes.
+        ZKB_ARG(random_poly != nullptr);
+        if (s->next_phase != pk->cs.nphases) { set_error("zkb_prove_finish: advice phases incomplete"); return ZKB_ERR_STATE; }
+        ZKB_ARG((pk->nsets == 0 || z_blinds) && (pk->cs.lookups.empty() || phi_blinds));
+        ZKB_CUDA(cudaSetDevice(pk->ctx->device));
+        ZKB_TRY(prove_finish_impl(s, z_blinds, phi_blinds, random_poly));
+    }
     *proof_len = s->proof.size();
     if (proof_out) {
-        ZKB_ARG(proof_cap >= s->proof.size());
+        if (proof_cap < s->proof.size()) { set_error("zkb_prove_finish: buffer of %llu bytes, proof has %llu (kept in the session: call again)",
+                                                     (unsigned long long)proof_cap, (unsigned long long)s->proof.size()); return ZKB_ERR_ARG; }
         memcpy(proof_out, s->proof.data(), s->proof.size());
     }
     return ZKB_OK;

@@ -33,11 +33,22 @@ SIGNATURES = {
     "zkb_d2h": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64]),
     "zkb_ntt_fr_host": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint32, _vp, _vp, ctypes.c_int32]),
     "zkb_ntt_fr_dev": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint32, _vp, _vp, ctypes.c_int32, _vp]),
+    "zkb_ntt_fr_batch_dev": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, ctypes.c_int32, _vp]),
     "zkb_fr_root_of_unity": (ctypes.c_int32, [ctypes.c_uint32, _vp, _vp]),
     "zkb_msm_g1_host": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "zkb_msm_g1_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp]),
     "zkb_msm_g1_batch_dev": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint64, _vp, _vp]),
     "zkb_msm_last_adds": (ctypes.c_uint64, [_vp]),
+    "zkb_msm_last_levels": (ctypes.c_uint32, [_vp]),
+    "zkb_srs_load": (ctypes.c_int32, [_vp, ctypes.c_uint32, _vp, _vp, ctypes.POINTER(_vp)]),
+    "zkb_srs_load_dev": (ctypes.c_int32, [_vp, ctypes.c_uint32, _vp, _vp, ctypes.POINTER(_vp)]),
+    "zkb_srs_destroy": (ctypes.c_int32, [_vp]),
+    "zkb_srs_k": (ctypes.c_uint32, [_vp]),
+    "zkb_srs_downsize": (ctypes.c_int32, [_vp, ctypes.c_uint32, ctypes.POINTER(_vp)]),
+    "zkb_srs_read": (ctypes.c_int32, [_vp, ctypes.c_int32, _vp]),
+    "zkb_srs_commit_dev": (ctypes.c_int32, [_vp, ctypes.c_int32, _vp, ctypes.c_uint64, _vp, _vp, _vp]),
+    "zkb_srs_commit_host": (ctypes.c_int32, [_vp, ctypes.c_int32, _vp, ctypes.c_uint64, _vp, _vp]),
+    "zkb_srs_commit_batch_dev": (ctypes.c_int32, [_vp, ctypes.c_int32, _vp, ctypes.c_uint32, ctypes.c_uint64, _vp, _vp]),
     "zkb_g1_fixed_base_mul_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
     "zkb_field_binop_dev": (ctypes.c_int32, [_vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_uint64, _vp]),
     "zkb_field_unop_dev": (ctypes.c_int32, [_vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, ctypes.c_uint64, _vp]),
@@ -53,6 +64,9 @@ SIGNATURES = {
     "zkb_comm_init": (ctypes.c_int32, [_vp, _vp, ctypes.c_int32, ctypes.c_int32]),
     "zkb_comm_destroy": (ctypes.c_int32, [_vp]),
     "zkb_pk_create": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "zkb_pk_create_with_srs": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "zkb_keygen_pk": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, _vp, _vp, ctypes.c_uint64, _vp, ctypes.POINTER(_vp)]),
+    "zkb_pk_sigma_read": (ctypes.c_int32, [_vp, ctypes.c_uint32, _vp]),
     "zkb_pk_destroy": (ctypes.c_int32, [_vp]),
     "zkb_pk_vk_bytes": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
     "zkb_csf_validate": (ctypes.c_int32, [_vp, ctypes.c_uint64]),

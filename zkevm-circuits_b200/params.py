@@ -109,3 +109,76 @@ class ParamsKZG:
 
     def commit(self, coeffs_dev):
         return A.best_multiexp_dev(coeffs_dev, self.g[: coeffs_dev.shape[0]].contiguous())
+
+    def load(self, ctx=None, derive_lagrange=False):
+        """-> Srs: the device-resident handle (zkb_srs_load); shared by every ProvingKey created from it."""
+        return Srs.from_params(self, ctx=ctx, derive_lagrange=derive_lagrange)
+
+
+class Srs:
+    """zkb_srs handle: ParamsKZG resident on one GPU (prover/src/common/prover.rs:37-57 keeps one per degree and downsizes)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    @staticmethod
+    def from_params(params, ctx=None, derive_lagrange=False):
+        import ctypes
+        from .lib import check, default_context
+        ctx = ctx or default_context()
+        h = ctypes.c_void_p()
+        g, gl = params.g, (None if derive_lagrange else params.g_lagrange)
+        if isinstance(g, np.ndarray):
+            g = np.ascontiguousarray(g)
+            glp = np.ascontiguousarray(gl) if gl is not None else None
+            check(ctx.lib.zkb_srs_load(ctx.handle, params.k, ctypes.c_void_p(g.ctypes.data), ctypes.c_void_p(glp.ctypes.data) if glp is not None else None,
+                                       ctypes.byref(h)))
+        else:
+            A.sync_current_stream()
+            check(ctx.lib.zkb_srs_load_dev(ctx.handle, params.k, ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(gl.data_ptr()) if gl is not None else None,
+                                           ctypes.byref(h)))
+        return Srs(ctx, h)
+
+    @property
+    def k(self):
+        return int(self.ctx.lib.zkb_srs_k(self.handle))
+
+    def downsize(self, new_k):
+        """ParamsKZG::downsize: g truncated, g_lagrange recomputed by the group iFFT on the device."""
+        import ctypes
+        from .lib import check
+        h = ctypes.c_void_p()
+        check(self.ctx.lib.zkb_srs_downsize(self.handle, int(new_k), ctypes.byref(h)))
+        return Srs(self.ctx, h)
+
+    def read(self, basis):
+        """basis 0 = g, 1 = g_lagrange -> uint64 (n, 8) host array."""
+        import ctypes
+        from .lib import check
+        out = np.empty((1 << self.k, 8), dtype=np.uint64)
+        check(self.ctx.lib.zkb_srs_read(self.handle, int(basis), ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def _commit(self, basis, scalars_dev):
+        import ctypes
+        from .lib import check
+        out = np.zeros(8, dtype=np.uint64)
+        comp = (ctypes.c_uint8 * 32)()
+        check(self.ctx.lib.zkb_srs_commit_dev(self.handle, basis, ctypes.c_void_p(scalars_dev.data_ptr()), scalars_dev.shape[0],
+                                              ctypes.c_void_p(out.ctypes.data), ctypes.cast(comp, ctypes.c_void_p), A._cur_stream()))
+        return A.MsmResult(out, None, bytes(comp))
+
+    def commit(self, coeffs_dev):
+        return self._commit(0, coeffs_dev)
+
+    def commit_lagrange(self, values_dev):
+        return self._commit(1, values_dev)
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.zkb_srs_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass

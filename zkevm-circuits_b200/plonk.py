@@ -117,19 +117,38 @@ def _ptr_array(arrs):
 class ProvingKey:
     """plonk::ProvingKey<G1Affine> material resident on the GPU (keygen itself stays with the caller: SURVEY 8f row 3)."""
 
-    def __init__(self, cs, fixed_values, sigma_values, g, g_lagrange, ctx=None):
-        self.ctx = ctx or default_context()
+    def __init__(self, cs, fixed_values, sigma_values, g=None, g_lagrange=None, ctx=None, srs=None, copies=None):
+        """Either (g, g_lagrange) host arrays [legacy: the pk uploads its own SRS] or srs = params.Srs handle (shared).
+        copies != None: keygen path (zkb_keygen_pk) -- sigma_values is ignored and the permutation is assembled from the copy
+        constraints [(left perm column, left row, right perm column, right row), ...]."""
+        self.ctx = ctx or (srs.ctx if srs is not None else default_context())
         self.cs = cs
+        self.srs = srs
         n = cs.n
-        assert g.shape == (n, 8) and g_lagrange.shape == (n, 8)
         blob = cs.to_csf()
         kf, ftbl = _ptr_array(fixed_values)
-        ks, stbl = _ptr_array(sigma_values)
-        g = np.ascontiguousarray(g); gl = np.ascontiguousarray(g_lagrange)
         h = _vp()
-        check(self.ctx.lib.zkb_pk_create(self.ctx.handle, _vp(blob.ctypes.data), blob.size, ctypes.cast(ftbl, _vp), ctypes.cast(stbl, _vp),
-                                         _vp(g.ctypes.data), _vp(gl.ctypes.data), ctypes.byref(h)))
+        if copies is not None:
+            assert srs is not None
+            cp = np.ascontiguousarray(np.asarray(copies, dtype=np.uint32).reshape(-1, 4))
+            check(self.ctx.lib.zkb_keygen_pk(self.ctx.handle, _vp(blob.ctypes.data), blob.size, ctypes.cast(ftbl, _vp), _vp(cp.ctypes.data), cp.shape[0],
+                                             srs.handle, ctypes.byref(h)))
+        elif srs is not None:
+            ks, stbl = _ptr_array(sigma_values)
+            check(self.ctx.lib.zkb_pk_create_with_srs(self.ctx.handle, _vp(blob.ctypes.data), blob.size, ctypes.cast(ftbl, _vp), ctypes.cast(stbl, _vp),
+                                                      srs.handle, ctypes.byref(h)))
+        else:
+            assert g.shape == (n, 8) and g_lagrange.shape == (n, 8)
+            ks, stbl = _ptr_array(sigma_values)
+            g = np.ascontiguousarray(g); gl = np.ascontiguousarray(g_lagrange)
+            check(self.ctx.lib.zkb_pk_create(self.ctx.handle, _vp(blob.ctypes.data), blob.size, ctypes.cast(ftbl, _vp), ctypes.cast(stbl, _vp),
+                                             _vp(g.ctypes.data), _vp(gl.ctypes.data), ctypes.byref(h)))
         self.handle = h
+
+    def sigma_values(self, column):
+        out = np.empty((self.cs.n, 4), dtype=np.uint64)
+        check(self.ctx.lib.zkb_pk_sigma_read(self.handle, int(column), _vp(out.ctypes.data)))
+        return out
 
     def vk_bytes(self):
         """VerifyingKey::to_bytes(SerdeFormat::Processed): fixed + permutation commitments computed on the GPU."""
@@ -186,10 +205,11 @@ def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blind
         pb = np.ascontiguousarray(phi_blinds) if phi_blinds is not None and len(phi_blinds) else None
         rp = np.ascontiguousarray(random_poly)
         plen = ctypes.c_uint64(0)
-        cap = 1 << 20
-        out = (ctypes.c_uint8 * cap)()
+        # first call runs the proof and reports its length (bytes stay in the session); second call copies them out
         check(lib.zkb_prove_finish(sess, _vp(zb.ctypes.data) if zb is not None else None, _vp(pb.ctypes.data) if pb is not None else None,
-                                   _vp(rp.ctypes.data), ctypes.cast(out, _vp), cap, ctypes.byref(plen)))
+                                   _vp(rp.ctypes.data), None, 0, ctypes.byref(plen)))
+        out = (ctypes.c_uint8 * max(1, plen.value))()
+        check(lib.zkb_prove_finish(sess, None, None, None, ctypes.cast(out, _vp), plen.value, ctypes.byref(plen)))
         return bytes(out[: plen.value])
     finally:
         lib.zkb_session_destroy(sess)

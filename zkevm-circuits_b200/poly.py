@@ -52,3 +52,16 @@ def kate_division_dev(a, u, ctx=None):
     uk, up = _limbs_ptr(u)
     check(ctx.lib.zkb_kate_division_dev(ctx.handle, _vp(a.data_ptr()), a.shape[0], up, _vp(out.data_ptr()), _cur_stream()))
     return out
+
+
+def ntt_batch_dev(cols, omega, log_n, scale=None, coset_zeta=0, ctx=None):
+    """In-place best_fft of several device columns (list of (n,4) int64 CUDA tensors) in one launch per pass; returns the list."""
+    import ctypes
+    import numpy as np
+    from .arithmetic import _cur_stream, _limbs_ptr
+    ctx = ctx or default_context(cols[0].device.index)
+    ptrs = (ctypes.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
+    kw, wp = _limbs_ptr(omega)
+    ks, sp = _limbs_ptr(scale) if scale is not None else (None, None)
+    check(ctx.lib.zkb_ntt_fr_batch_dev(ctx.handle, ctypes.cast(ptrs, ctypes.c_void_p), len(cols), log_n, wp, sp, coset_zeta, _cur_stream()))
+    return cols
