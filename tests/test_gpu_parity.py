@@ -275,19 +275,30 @@ def test_msm_2_23_linearity(A, oracle):
 
 
 def test_msm_reduction_levels_decided_on_device(A, oracle):
-    """random scalars: the chunked level 0 leaves at most a few partials per bucket (one extra level); a column whose scalars are all
-    equal piles everything into one bucket per window and needs more levels -- the host never learns the counts."""
+    """The reduction levels after the chunked level 0 are decided on the device (the host never learns the bucket sizes).  Random
+    scalars: buckets hold ~32 entries (two or three 32-entry chunks), but the TOP window sees only the two leading bits of a
+    254-bit scalar, so four buckets collect n/4 entries each -> 512 partials -> two 64-way levels at n = 2^16.  All-equal scalars
+    put all n entries of every window into one bucket (2048 partials): also two levels.  n = 2^11 needs one level at most for
+    either.  Results are compared with the oracle in every case."""
     from zkb200 import default_context
+    ctx = default_context()
+    levels = lambda: ctx.lib.zkb_msm_last_levels(ctx.handle)
     n = 1 << 16
     bases = make_bases(A, oracle, n, 777)
     bt = to_dev(bases)
-    r = A.best_multiexp_dev(to_dev(rand_field(n, 778)), bt)
-    lv_random = default_context().lib.zkb_msm_last_levels(default_context().handle)
+    rnd = rand_field(n, 778)
+    r = A.best_multiexp_dev(to_dev(rnd), bt)
+    lv_random = levels()
+    assert (r.affine == oracle.g1_to_affine(oracle.best_multiexp(rnd, bases))).all()
     same = np.repeat(rand_field(1, 779), n, axis=0)
     r2 = A.best_multiexp_dev(to_dev(same), bt)
-    lv_skew = default_context().lib.zkb_msm_last_levels(default_context().handle)
+    lv_skew = levels()
     assert (r2.affine == oracle.g1_to_affine(oracle.best_multiexp(same, bases))).all()
-    assert lv_random <= 1 and lv_skew >= 2
+    assert lv_random == 2 and lv_skew == 2
+    m = 1 << 11
+    r3 = A.best_multiexp_dev(to_dev(same[:m]), bt[:m])
+    assert levels() == 1     # 2048 entries in one bucket -> 64 partials -> one level
+    assert (r3.affine == oracle.g1_to_affine(oracle.best_multiexp(same[:m], bases[:m]))).all()
 
 
 @pytest.mark.parametrize("k", [6, 10])

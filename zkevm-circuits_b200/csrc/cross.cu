@@ -6,7 +6,7 @@
 //   step A : local size-M NTT with omega^P                       (existing kernels)
 //   step B : multiply element t by omega^(r t)                   (fr_powers + element-wise multiply)
 //   step C : ONE all-to-all: rank s receives, from every rank j, the block t in [s M/P, (s+1) M/P)
-//   step D : zkb_ntt_cross_dev: out[k][t] = sum_j in[j][t] * omega_P^(j k)  (this file; P^2 multiplies per t, P <= 16)
+//   step D : zkb_ntt_cross_dev: out[k][t] = sum_j in[j][t] * omega_P^(j k)  (this file; log2 P radix-2 stages in registers, P <= 16)
 //   output : rank s holds X[k M + s M/P + t] for k < P, t < M/P  ("strips"; zkb200.parallel.strips_to_natural documents it)
 // MSM shards by point range (no exchange of points); partial sums are all-gathered as 64-byte affine points and added
 // with zkb_g1_sum_affine_host (pure host code, also usable on a box without a GPU).
@@ -17,6 +17,8 @@ namespace zkb {
 
 struct CrossTw { Fr w[16]; };  // omega_P^i, i < P
 
+// log2(P) radix-2 decimation-in-frequency stages in registers: (P/2) log2 P multiplies per t (12 at P = 8, 32 at P = 16; the
+// earlier direct O(P^2) form needed 56 / 240 and spilled); outputs leave in bit-reversed register order.
 template <int P>
 __global__ void __launch_bounds__(128) ntt_cross_kernel(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t len, CrossTw tw) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -25,14 +27,25 @@ __global__ void __launch_bounds__(128) ntt_cross_kernel(const Fr *__restrict__ i
 #pragma unroll
     for (int j = 0; j < P; ++j) v[j] = fp_load(in + (size_t)j * len + t);
 #pragma unroll
-    for (int k = 0; k < P; ++k) {
-        Fr acc = v[0];
+    for (int half = P / 2; half >= 1; half >>= 1) {
 #pragma unroll
-        for (int j = 1; j < P; ++j) {
-            const int e = (j * k) % P;
-            acc = fp_add(acc, e == 0 ? v[j] : fp_mul(v[j], tw.w[e]));
+        for (int b = 0; b < P; b += 2 * half) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const Fr u = v[b + j], w = v[b + j + half];
+                v[b + j] = fp_add(u, w);
+                const Fr d = fp_sub(u, w);
+                const int e = j * (P / (2 * half));   // omega_P^e
+                v[b + j + half] = e == 0 ? d : fp_mul(d, tw.w[e]);
+            }
         }
-        fp_store(out + (size_t)k * len + t, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        int k = 0;
+#pragma unroll
+        for (int bit = 1, rb = P >> 1; bit < P; bit <<= 1, rb >>= 1) if (i & bit) k |= rb;
+        fp_store(out + (size_t)k * len + t, v[i]);
     }
 }
 
