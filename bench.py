@@ -270,7 +270,8 @@ def main():
 
     # roofline of the dominant kernel (ntt_pass_kernel): 2 launches per transform, each reads + writes the array once.
     # Algorithmic bytes of a transform = 2*32*n; one launch does half of a transform's passes.
-    pass_launches = 4 * K                      # 2 per direction
+    pass_launches = launches                    # ntt_tile_kernel launches inside the timed region (3 passes per direction at 2^24)
+    passes_per_dir = pass_launches // (2 * K)
     avg_launch_s = (ms_total * 1e-3) / pass_launches
     peaks = {}
     try:
@@ -278,8 +279,8 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = (ALG_BYTES_PER_DIR / 2) / avg_launch_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    achieved = (ALG_BYTES_PER_DIR / passes_per_dir) / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "ntt_tile_kernel", "launches_per_transform": passes_per_dir, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                 # dram__bytes_read.sum + dram__bytes_write.sum per ntt_pass_kernel launch at 2^24, averaged over the two passes of a
                 # transform (ncu --set full, profiles/r01_ntt_pass_v3_final_ncu.txt): pass 1 = 1074 MB read (537 MB data + 537 MB

@@ -28,18 +28,23 @@ def swz(i):
 
 
 class Plan:
-    def __init__(self, log_n, tile_bits, max_bits):
+    def __init__(self, log_n, tile_bits, max_bits, pref_inner_bits=None, max_inner_bits=None):
+        """max_bits bounds the final pass (NTT_MAX_BITS), pref_inner_bits the others (NTT_PREF_INNER_BITS), relaxed to max_inner_bits
+        (NTT_MAX_INNER_BITS) only when three passes would not reach log_n otherwise."""
+        pi = max_bits if pref_inner_bits is None else pref_inner_bits
+        mi = pi if max_inner_bits is None else max_inner_bits
         self.log_n, self.tile_bits, self.max_bits = log_n, tile_bits, max_bits
         if log_n <= max_bits:
             self.bits = [log_n]
-        elif log_n <= 2 * max_bits:
-            b0 = (log_n + 1) // 2
+        elif log_n <= pi + max_bits:
+            b0 = min(pi, (log_n + 1) // 2)
             self.bits = [b0, log_n - b0]
         else:
-            b0 = (log_n + 2) // 3
-            b1 = (log_n - b0 + 1) // 2
+            cap = mi if log_n > 2 * pi + max_bits else pi
+            b0 = min(cap, (log_n + 2) // 3)
+            b1 = min(cap, (log_n - b0 + 1) // 2)
             self.bits = [b0, b1, log_n - b0 - b1]
-        assert all(b <= max_bits for b in self.bits)
+        assert all(b <= mi for b in self.bits[:-1]) and self.bits[-1] <= max_bits
         self.npass = len(self.bits)
 
     def geom(self, ps):
@@ -103,12 +108,13 @@ def run_pass(plan, ps, src, dst, omega, threads, coset_in=None, in_scale=None, s
                     L0[(c << a) + r] = src[(sub << a) + r]
         L1 = [None] * (C * (A + 1))
         # ---- rounds
-        def ntt_round(R, first, s):
+        def ntt_round(R, first, last, s):
             E = 1 << R
             NG = per_thread // E
             total_groups = elems >> R
             lgpc = a - R
-            lq = a - s - R
+            lq = 0 if last else a - s - R
+            assert lq == a - s - R
             q = 1 << lq
             regs = {}
             for tid in range(threads):
@@ -141,32 +147,38 @@ def run_pass(plan, ps, src, dst, omega, threads, coset_in=None, in_scale=None, s
                             uu, vv = x[m], x[m + d]
                             x[m] = (uu + vv) % R_MOD
                             dif = (uu - vv) % R_MOD
-                            if not trivial:
+                            if last:
+                                if (m & (d - 1)) != 0:
+                                    dif = dif * loc[(m & (d - 1)) << (s + t)] % R_MOD
+                            elif not trivial:
                                 pos = ploc + ((m & (d - 1)) << lq)
                                 dif = dif * loc[pos << (s + t)] % R_MOD
                             x[m + d] = dif
                 for m in range(E):
                     r = rbase + (m << lq)
                     L1[c * (A + 1) + swz(r)] = x[m]
-        s = 0
-        if a >= 3:
-            ntt_round(3, True, 0); s = 3
+        if a == 0:
+            ntt_round(0, True, False, 0)
         else:
-            ntt_round(0, True, 0)
-        while a - s >= 3:
-            ntt_round(3, False, s); s += 3
-        if a - s == 2: ntt_round(2, False, s)
-        elif a - s == 1: ntt_round(1, False, s)
-        # ---- store phase
-        for tid in range(threads):
-            for u in range(per_thread):
+            r0 = a % 3 if a % 3 else 3
+            ntt_round(r0, True, False, 0)
+            s = r0
+            while a - s > 3:
+                ntt_round(3, False, False, s); s += 3
+            if a - s == 3:
+                ntt_round(3, False, True, s)
+        # ---- store phase (non-final: the boundary-table tile arrives in chunks of one store iteration through the ring)
+        chunk_elems = min(elems, threads)
+        nchunks = elems // chunk_elems
+        for u in range(nchunks if not is_final else per_thread):
+            for tid in range(threads):
                 e = tid + u * threads
-                if e >= elems: continue
+                if (tid >= chunk_elems) if not is_final else (e >= elems): continue
                 c, q = e & (C - 1), e >> log_c
                 k = brev(q, a)
                 v = L1[c * (A + 1) + swz(q)]
                 if not is_final:
-                    v = v * tw[blk * elems + e] % R_MOD
+                    v = v * tw[blk * elems + u * chunk_elems + tid] % R_MOD
                     oidx = ((((outer << a) + k)) << log_inner) + c0 + c
                 else:
                     oidx = c0 + c + (outer << a1) + (k << (a1 + a2))
@@ -177,9 +189,9 @@ def run_pass(plan, ps, src, dst, omega, threads, coset_in=None, in_scale=None, s
                 dst[oidx] = v
 
 
-def ntt(values, log_n, omega, tile_bits, max_bits, threads, scale=None, coset_zeta=0, zeta=None, in_scale=None):
+def ntt(values, log_n, omega, tile_bits, max_bits, threads, scale=None, coset_zeta=0, zeta=None, in_scale=None, pref_inner_bits=None, max_inner_bits=None):
     """Mirror of ntt_fr_batch_device for one column."""
-    plan = Plan(log_n, tile_bits, max_bits)
+    plan = Plan(log_n, tile_bits, max_bits, pref_inner_bits, max_inner_bits)
     n = 1 << log_n
     scratch = [None] * n
     out = [None] * n

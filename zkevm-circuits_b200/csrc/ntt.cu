@@ -5,21 +5,25 @@
 // extended_to_coeff}).  Same contract: in place, natural order in / natural order out, a'[k] = sum_j a[j] w^(jk).
 //
 // B200 design (NOT upstream's bit-reverse + log n global layers):
-//   n = A1 * A2 (* A3), every factor <= 2^11 (1 pass up to 2^11, 2 passes up to 2^22, 3 passes above).  A pass is ONE
-//   persistent kernel (one CTA per SM) that walks over TILES of 2048 elements (64 KB): a tile is C = 2048 / A adjacent
-//   columns of the Cooley-Tukey index split, i.e. C independent length-A transforms whose rows are C*32 contiguous bytes in
-//   HBM.  Per tile:
+//   n = A1 * A2 (* A3): 1 pass up to 2^10, 2 passes up to 2^18, 3 passes above (non-final factors <= 2^8, final <= 2^10; 2^9 from
+//   2^27).  A pass is ONE persistent kernel, FOUR 128-thread CTAs per SM, each walking over TILES of 1024 elements (32 KB): a tile
+//   is C = 1024 / A adjacent columns of the Cooley-Tukey index split, i.e. C independent length-A transforms whose rows are C*32
+//   contiguous bytes in HBM.  The four resident CTAs run out of phase, so while one waits for TMA data, converts layouts or
+//   streams results out, the others are in their multiplier-bound butterfly rounds: the integer-multiply pipe (the bound, see
+//   DESIGN.md) stays fed.  Per tile:
 //     * the data tile is fetched by TMA (cp.async.bulk.tensor.2d through a per-column tensor map: box = 256 rows x 32 B;
-//       the contiguous tiles of the last pass by cp.async.bulk) into one of TWO shared-memory buffers, one tile AHEAD of
-//       the arithmetic, completion signalled on an mbarrier (complete_tx::bytes);
-//     * the tile's inter-pass twiddles w_n^(j_in * k) are a TMA-staged tile as well: the table is stored tile-major in the
-//       order the tile consumes it, so one 64 KB cp.async.bulk brings them in while the butterflies run;
+//       the contiguous sub-transforms of the last pass by cp.async.bulk), completion signalled on an mbarrier
+//       (complete_tx::bytes); the fetch of tile i+1 is issued the moment tile i's last result left shared memory;
+//     * the tile's inter-pass twiddles w_n^(j_in * k) are TMA-staged as well: the table is stored tile-major in the order the
+//       store phase consumes it and streams through a ring of four 4 KB slots (one slot = the 128 elements of one store
+//       iteration), refilled four iterations ahead -- across the tile boundary, so the next tile's first twiddles are already
+//       resident while its butterflies run;
 //     * the A/2 local twiddles of the pass sit in shared memory for the life of the CTA (one bulk copy at kernel start);
-//     * decimation in frequency in radix-8 rounds held in registers (8 elements / thread / round, 256 threads, no spills),
-//       two 16-byte planes with an XOR swizzle + one padding slot per column -> conflict-free 128-bit LDS/STS;
+//     * decimation in frequency in radix-8 rounds held in registers (8 elements / thread / round, 128 threads), the short round
+//       first and a radix-8 round last, where the unit twiddles (3 of 8 per thread, plus the whole last stage) are known at
+//       compile time and cost no multiply: (A/2) log2 A - (A - 1) + A/8 multiplies per transform instead of (A/2) log2 A;
+//     * two 16-byte planes with an XOR swizzle + one padding slot per column -> conflict-free 128-bit LDS/STS;
 //     * results leave through 32-byte streaming stores, C adjacent threads writing C*32 contiguous bytes.
-//   The multiplier pipe (1 Montgomery multiply = 139 IMAD.WIDE per butterfly) is the bound, not HBM: the TMA pipeline keeps
-//   it fed during what used to be the load and store phases of a single resident CTA.
 //   Scaling by 1/n (any caller scale) is folded into the last inter-pass table; zeta-coset scaling and an arbitrary
 //   per-element input scale are fused into the first / last register round.
 #include "common.cuh"
@@ -29,14 +33,19 @@
 
 namespace zkb {
 
-constexpr int NTT_TILE_BITS = 11;   // 2048 elements = 64 KB per tile
-constexpr int NTT_MAX_BITS = 11;    // largest in-CTA transform
-constexpr int NTT_THREADS = 256;    // 8 elements per thread and round
+constexpr int NTT_TILE_BITS = 10;        // 1024 elements = 32 KB per tile
+constexpr int NTT_MAX_BITS = 10;         // largest in-CTA transform (final pass: no twiddle ring in shared memory)
+constexpr int NTT_PREF_INNER_BITS = 8;   // non-final passes: 4 KB of local twiddles next to the 16 KB twiddle ring -> four CTAs per SM
+constexpr int NTT_MAX_INNER_BITS = 9;    // only for log_n >= 27 (8 KB of local twiddles: three resident CTAs)
+constexpr int NTT_THREADS = 128;         // 8 elements per thread and round
+constexpr int NTT_CTAS_PER_SM = 4;
 constexpr int TW_LO_BITS = 12;
 constexpr uint32_t NTT_BOX_ROWS = 256;
-constexpr uint32_t NTT_HDR_BYTES = 128;                                  // mbarriers
-constexpr uint32_t NTT_DBUF_BYTES = 32u * ((1u << NTT_TILE_BITS) + 32u);  // two 16-byte planes of C*(A+1) <= 2048+32 slots
-constexpr uint32_t NTT_TWBUF_BYTES = 32u << NTT_TILE_BITS;
+constexpr uint32_t NTT_HDR_BYTES = 128;                                  // mbarriers: [0] data, [1] local twiddles, [2..5] ring slots
+constexpr uint32_t NTT_DBUF_BYTES = 32u * ((1u << NTT_TILE_BITS) + 32u);  // two 16-byte planes of C*(A+1) <= 1024+32 slots (A >= 32 in multi-pass plans)
+constexpr uint32_t NTT_TW_SLOTS = 4;
+constexpr uint32_t NTT_TW_SLOT_ELEMS = NTT_THREADS;                       // one store iteration
+constexpr uint32_t NTT_TW_RING_BYTES = NTT_TW_SLOTS * NTT_TW_SLOT_ELEMS * 32u;
 
 // ZETA = 7^((r-1)/3) and ZETA^2 (Montgomery form); EvaluationDomain::g_coset / g_coset_inv (poly/domain.rs)
 __device__ __constant__ uint32_t ZETA_POW[2][8];
@@ -144,14 +153,16 @@ __device__ __forceinline__ Fr zeta_pow(int i) {  // i in {1,2}
 // R consecutive DIF stages (s .. s+R-1) on groups of 2^R elements held in registers: one shared-memory round trip and one
 // barrier per R stages.  Every thread owns 8 element slots per round (8 / 2^R groups).  FIRST: the inputs are read from the
 // TMA layout L0 (with the fused input scalings), then -- after a barrier, the conversion is in place -- written in L1.
-template <int R, bool FIRST>
+// LAST (s + R == a): the group's elements are adjacent rows, so the twiddle exponents depend on the register index alone and the
+// unit twiddles (m & (d - 1)) == 0 are dropped at compile time.
+template <int R, bool FIRST, bool LAST>
 __device__ __forceinline__ void ntt_round(uint8_t *dbuf, const PassArgs &p, const TileInfo &ti, uint32_t s, const uint8_t *loc_sm, uint32_t tid) {
     constexpr int E = 1 << R, NG = 8 / E;
     const uint32_t a = p.a, A = 1u << a;
     const uint32_t elems = 1u << (a + p.log_c);
     const uint32_t total_groups = elems >> R;
-    const uint32_t lgpc = a - R;           // log2 (groups per column)
-    const uint32_t lq = a - s - R;         // log2 of the spacing of a group's elements (half distance of the round's last stage)
+    const uint32_t lgpc = a - R;                     // log2 (groups per column)
+    const uint32_t lq = LAST ? 0u : a - s - R;       // log2 of the spacing of a group's elements (half distance of the round's last stage)
     const uint32_t q = 1u << lq;
     uint4 *lo = reinterpret_cast<uint4 *>(dbuf);
     uint4 *hi = lo + ((A + 1) << p.log_c);
@@ -203,7 +214,9 @@ __device__ __forceinline__ void ntt_round(uint8_t *dbuf, const PassArgs &p, cons
                     const Fr uu = x[u * E + m], vv = x[u * E + m + d];
                     x[u * E + m] = fp_add(uu, vv);
                     Fr dif = fp_sub(uu, vv);
-                    if (!last_trivial) {
+                    if (LAST) {
+                        if ((m & (d - 1)) != 0) dif = fp_mul(dif, ld_lin(loc_sm, (uint32_t)(m & (d - 1)) << (s + t)));
+                    } else if (!last_trivial) {
                         const uint32_t pos = ploc[u] + ((uint32_t)(m & (d - 1)) << lq);
                         dif = fp_mul(dif, ld_lin(loc_sm, pos << (s + t)));
                     }
@@ -238,28 +251,36 @@ __device__ __forceinline__ void issue_data(const PassArgs &p, uint32_t gt, uint3
         }
     }
 }
-__device__ __forceinline__ void issue_tw(const PassArgs &p, uint32_t gt, uint32_t dst, uint32_t bar) {
+// thread 0: stage chunk `chunk` (chunk_elems twiddles) of tile gt's boundary-table tile into ring slot memory `dst`
+__device__ __forceinline__ void issue_tw(const PassArgs &p, uint32_t gt, uint32_t chunk, uint32_t chunk_elems, uint32_t dst, uint32_t bar) {
     const TileInfo t = decode_tile(p, gt);
-    const uint32_t bytes = 32u << (p.a + p.log_c);
+    const uint32_t bytes = chunk_elems * 32u;
     mbar_expect_tx(bar, bytes);
-    tma_load_bulk(dst, p.tw + ((size_t)t.tw_tile << (p.a + p.log_c)), bytes, bar);
+    tma_load_bulk(dst, p.tw + ((size_t)t.tw_tile << (p.a + p.log_c)) + (size_t)chunk * chunk_elems, bytes, bar);
 }
 
-__global__ void __launch_bounds__(NTT_THREADS, 1) ntt_tile_kernel(const __grid_constant__ PassArgs p) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_CTAS_PER_SM) ntt_tile_kernel(const __grid_constant__ PassArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tid = threadIdx.x;
     const uint32_t a = p.a, A = 1u << a, C = 1u << p.log_c, elems = A << p.log_c;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // [0],[1] data buffers, [2] twiddle tile, [3] local twiddles
-    uint8_t *twbuf = smem + NTT_HDR_BYTES + 2 * NTT_DBUF_BYTES;
-    uint8_t *locbuf = twbuf + (p.is_final ? 0u : NTT_TWBUF_BYTES);
-    const uint32_t bar_d[2] = {smem_u32(bars), smem_u32(bars + 1)};
-    const uint32_t bar_tw = smem_u32(bars + 2), bar_loc = smem_u32(bars + 3);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // [0] data buffer, [1] local twiddles, [2 .. 5] twiddle ring slots
+    uint8_t *d = smem + NTT_HDR_BYTES;
+    uint8_t *twring = d + NTT_DBUF_BYTES;
+    uint8_t *locbuf = twring + (p.is_final ? 0u : NTT_TW_RING_BYTES);
+    const uint32_t bar_d = smem_u32(bars), bar_loc = smem_u32(bars + 1), bar_tw0 = smem_u32(bars + 2);
     const uint32_t stride = gridDim.x;
     uint32_t gt = blockIdx.x;
     if (gt >= p.total_tiles) return;
+    // the boundary-table tile is consumed in chunks of one store iteration (256 elements; a whole short tile at once)
+    const uint32_t chunk_elems = elems < NTT_TW_SLOT_ELEMS ? elems : NTT_TW_SLOT_ELEMS;
+    const uint32_t nchunks = elems / chunk_elems;
+    // thread 0 only: position of the next chunk to stage (walks this CTA's tile sequence), and its running number
+    uint32_t is_gt = gt, is_c = 0, is_g = 0;
+    uint32_t g_wait = 0;   // running number of the next chunk to consume: slot = g & 3, parity = (g >> 2) & 1
 
     if (tid == 0) {
-        mbar_init(bar_d[0], 1); mbar_init(bar_d[1], 1); mbar_init(bar_tw, 1); mbar_init(bar_loc, 1);
+        mbar_init(bar_d, 1); mbar_init(bar_loc, 1);
+        for (uint32_t j = 0; j < NTT_TW_SLOTS; ++j) mbar_init(bar_tw0 + 8 * j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -267,46 +288,60 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_tile_kernel(const __grid_c
         const uint32_t loc_bytes = (a ? (A >> 1) : 1u) * 32u;
         mbar_expect_tx(bar_loc, loc_bytes);
         tma_load_bulk(smem_u32(locbuf), p.loc, loc_bytes, bar_loc);
-        issue_data(p, gt, smem_u32(smem + NTT_HDR_BYTES), bar_d[0]);
-        if (!p.is_final) issue_tw(p, gt, smem_u32(twbuf), bar_tw);
+        issue_data(p, gt, smem_u32(d), bar_d);
+        if (!p.is_final) {
+            for (; is_g < NTT_TW_SLOTS && is_gt < p.total_tiles; ++is_g) {
+                issue_tw(p, is_gt, is_c, chunk_elems, smem_u32(twring) + (is_g & 3u) * (NTT_TW_SLOT_ELEMS * 32u), bar_tw0 + 8 * (is_g & 3u));
+                if (++is_c == nchunks) { is_c = 0; is_gt += stride; }
+            }
+        }
     }
     mbar_wait(bar_loc, 0);
 
     for (uint32_t it = 0; gt < p.total_tiles; ++it, gt += stride) {
-        const uint32_t b = it & 1;
-        // the other buffer was released by the barrier that closed the previous iteration: fetch the next tile into it now
-        if (tid == 0 && gt + stride < p.total_tiles) issue_data(p, gt + stride, smem_u32(smem + NTT_HDR_BYTES + (b ^ 1) * NTT_DBUF_BYTES), bar_d[b ^ 1]);
         const TileInfo ti = decode_tile(p, gt);
-        uint8_t *d = smem + NTT_HDR_BYTES + b * NTT_DBUF_BYTES;
-        mbar_wait(bar_d[b], (it >> 1) & 1);
+        mbar_wait(bar_d, it & 1);
 
-        // decimation in frequency: natural order in, bit-reversed order out (inside shared memory); radix-8 rounds in registers
-        // (transforms shorter than 8 points first convert the TMA layout with the degenerate round<0>)
-        {
-            uint32_t s = 0;
-            if (a >= 3) { ntt_round<3, true>(d, p, ti, 0, locbuf, tid); s = 3; }
-            else ntt_round<0, true>(d, p, ti, 0, locbuf, tid);
+        // decimation in frequency: natural order in, bit-reversed order out (inside shared memory); radix-8 rounds in registers,
+        // the short round (a mod 3 stages) first, so that the last one is a full radix-8 round with compile-time unit twiddles
+        if (a == 0) {
+            ntt_round<0, true, false>(d, p, ti, 0, locbuf, tid);
             __syncthreads();
-            while (a - s >= 3) { ntt_round<3, false>(d, p, ti, s, locbuf, tid); __syncthreads(); s += 3; }
-            if (a - s == 2) { ntt_round<2, false>(d, p, ti, s, locbuf, tid); __syncthreads(); }
-            else if (a - s == 1) { ntt_round<1, false>(d, p, ti, s, locbuf, tid); __syncthreads(); }
+        } else {
+            const uint32_t r0 = a % 3 ? a % 3 : 3;
+            if (r0 == 1) ntt_round<1, true, false>(d, p, ti, 0, locbuf, tid);
+            else if (r0 == 2) ntt_round<2, true, false>(d, p, ti, 0, locbuf, tid);
+            else ntt_round<3, true, false>(d, p, ti, 0, locbuf, tid);
+            __syncthreads();
+            uint32_t s = r0;
+            while (a - s > 3) { ntt_round<3, false, false>(d, p, ti, s, locbuf, tid); __syncthreads(); s += 3; }
+            if (a - s == 3) { ntt_round<3, false, true>(d, p, ti, s, locbuf, tid); __syncthreads(); }
         }
 
         const uint4 *lo = reinterpret_cast<const uint4 *>(d);
         const uint4 *hi = lo + ((A + 1) << p.log_c);
         Fr *__restrict__ out = p.dst[ti.y];
         if (!p.is_final) {
-            mbar_wait(bar_tw, it & 1);
             // slot q of a column holds output k = bitrev(q); the staged table is [q][c] in exactly this order
-#pragma unroll 4
-            for (uint32_t u = 0; u < 8; ++u) {
+            for (uint32_t u = 0; u < nchunks; ++u, ++g_wait) {
+                const uint32_t slot = g_wait & 3u;
+                mbar_wait(bar_tw0 + 8 * slot, (g_wait >> 2) & 1u);
                 const uint32_t e = tid + u * NTT_THREADS;
-                if (e < elems) {
+                if (tid < chunk_elems) {
                     const uint32_t c = e & (C - 1), q = e >> p.log_c;
                     const uint32_t k = __brev(q) >> (32 - a);   // a >= 1 in non-final passes
-                    const Fr v = fp_mul(ld_l1(lo, hi, c * (A + 1) + swz(q)), ld_lin(twbuf, e));
+                    const Fr v = fp_mul(ld_l1(lo, hi, c * (A + 1) + swz(q)), ld_lin(twring + slot * (NTT_TW_SLOT_ELEMS * 32u), tid));
                     const uint64_t oidx = ((((uint64_t)ti.outer << a) + k) << p.log_inner) + ti.c0 + c;
                     fp_store_stream(out + oidx, v);
+                }
+                // generic-proxy reads of this slot (and, after the last iteration, of the data buffer) are ordered before the
+                // async-proxy (TMA) writes that reuse them
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0 && is_gt < p.total_tiles) {
+                    issue_tw(p, is_gt, is_c, chunk_elems, smem_u32(twring) + (is_g & 3u) * (NTT_TW_SLOT_ELEMS * 32u), bar_tw0 + 8 * (is_g & 3u));
+                    ++is_g;
+                    if (++is_c == nchunks) { is_c = 0; is_gt += stride; }
                 }
             }
         } else {
@@ -327,11 +362,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_tile_kernel(const __grid_c
                     fp_store_stream(out + oidx, v);
                 }
             }
+            fence_proxy_async();
+            __syncthreads();
         }
-        // generic-proxy accesses of this tile's buffers are ordered before the async-proxy (TMA) writes that reuse them
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0 && !p.is_final && gt + stride < p.total_tiles) issue_tw(p, gt + stride, smem_u32(twbuf), bar_tw);
+        if (tid == 0 && gt + stride < p.total_tiles) issue_data(p, gt + stride, smem_u32(d), bar_d);
     }
 }
 
@@ -415,9 +449,22 @@ static int32_t get_plan(zkb_ctx *ctx, uint32_t log_n, const Fr &omega, NttPlan *
 
     NttPlan plan;
     plan.log_n = log_n;
+    // factor sizes: the final pass may be as long as a tile (2^11), the others are bounded by the shared-memory budget of two
+    // resident CTAs (2^9); more, shorter passes cost no extra multiplies (every pass drops its A - 1 unit twiddles, which pays
+    // for the extra boundary multiply per element), only one more trip through HBM
     if (log_n <= NTT_MAX_BITS) { plan.npass = 1; plan.bits[0] = log_n; }
-    else if (log_n <= 2 * NTT_MAX_BITS) { plan.npass = 2; plan.bits[0] = (log_n + 1) / 2; plan.bits[1] = log_n - plan.bits[0]; }
-    else { plan.npass = 3; plan.bits[0] = (log_n + 2) / 3; plan.bits[1] = (log_n - plan.bits[0] + 1) / 2; plan.bits[2] = log_n - plan.bits[0] - plan.bits[1]; }
+    else if (log_n <= NTT_PREF_INNER_BITS + NTT_MAX_BITS) {
+        plan.npass = 2;
+        plan.bits[0] = std::min<int>(NTT_PREF_INNER_BITS, (log_n + 1) / 2);
+        plan.bits[1] = log_n - plan.bits[0];
+    } else {
+        const int cap = log_n > 2 * NTT_PREF_INNER_BITS + NTT_MAX_BITS ? NTT_MAX_INNER_BITS : NTT_PREF_INNER_BITS;
+        plan.npass = 3;
+        plan.bits[0] = std::min<int>(cap, (log_n + 2) / 3);
+        plan.bits[1] = std::min<int>(cap, (log_n - plan.bits[0] + 1) / 2);
+        plan.bits[2] = log_n - plan.bits[0] - plan.bits[1];
+    }
+    if (plan.bits[plan.npass - 1] > NTT_MAX_BITS) { set_error("log_n %u exceeds the three-pass limit", log_n); return ZKB_ERR_ARG; }
 
     const uint32_t lo_bits = log_n < TW_LO_BITS ? log_n : TW_LO_BITS;
     ZKB_TRY(upload_powers(ctx, omega, (size_t)1 << lo_bits, &plan.tw_lo));
@@ -480,20 +527,23 @@ static int32_t encode_column_map(CUtensorMap *m, const Fr *base, uint32_t log_n,
 }
 
 static uint32_t pass_smem_bytes(const PassGeom &g) {
-    return NTT_HDR_BYTES + 2 * NTT_DBUF_BYTES + (g.is_final ? 0u : NTT_TWBUF_BYTES) + (g.a ? (32u << (g.a - 1)) : 32u);
+    return NTT_HDR_BYTES + NTT_DBUF_BYTES + (g.is_final ? 0u : NTT_TW_RING_BYTES) + (g.a ? (32u << (g.a - 1)) : 32u);
 }
 
 // batch of `count` transforms: column y reads h_src[y], writes h_dst[y] (HOST arrays of device pointers; the arrays may alias,
 // h_src[y] == h_dst[y] is an in-place transform).
 int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_dst, uint32_t count, uint32_t log_n, const Fr &omega,
                             const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, cudaStream_t st) {
-    ZKB_ARG(log_n <= 3 * NTT_MAX_BITS && log_n <= 28 && count >= 1 && h_src && h_dst);
+    ZKB_ARG(log_n <= 28 && count >= 1 && h_src && h_dst);
     ZKB_ARG(coset_zeta >= 0 && coset_zeta <= 2);
     NttPlan *plan = nullptr;
     ZKB_TRY(get_plan(ctx, log_n, omega, &plan));
     if (!ctx->ntt_ready) {
         // per device (a context owns one device): opt in to the large dynamic shared-memory window, upload ZETA
-        ZKB_CUDA(cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        // four CTAs per SM: header + data tile + twiddle ring + 4 (8) KB of local twiddles (non-final) or <= 16 KB (final, no ring)
+        ZKB_CUDA(cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(NTT_HDR_BYTES + NTT_DBUF_BYTES + NTT_TW_RING_BYTES + (32u << (NTT_MAX_INNER_BITS - 1)))));
+        ZKB_CUDA(cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         Fr z = host_zeta(), z2 = fp_sqr(z);
         uint32_t h[2][8];
         for (int i = 0; i < 8; ++i) { h[0][i] = z.l[i]; h[1][i] = z2.l[i]; }
@@ -580,7 +630,8 @@ int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_d
         p.src = (const Fr *const *)(dblob + maps_bytes + (size_t)(2 * ps) * tbl_bytes);
         p.dst = (Fr *const *)(dblob + maps_bytes + (size_t)(2 * ps + 1) * tbl_bytes);
         ZKB_ARG((uint64_t)p.tiles_per_col * count < (1ull << 32));
-        const uint32_t grid = p.total_tiles < (uint32_t)ctx->sm_count ? p.total_tiles : (uint32_t)ctx->sm_count;
+        const uint32_t max_ctas = (uint32_t)ctx->sm_count * NTT_CTAS_PER_SM;
+        const uint32_t grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
         ntt_tile_kernel<<<grid, NTT_THREADS, pass_smem_bytes(g), st>>>(p);
         ctx->launches++;
     }
