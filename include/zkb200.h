@@ -162,6 +162,20 @@ ZKB_API int32_t zkb_ntt_cross_dev(zkb_ctx *ctx, const uint64_t *in_dev, uint64_t
                                   const uint64_t omega_p[4], void *stream);
 ZKB_API int32_t zkb_g1_sum_affine_host(const uint64_t *points, uint64_t count, uint64_t out_affine[8], uint8_t *out_compressed);
 
+/* zkb_ntt_fr_sharded_dev   ONE transform of size 2^log_n spread over the ranks of the communicator (north_star: "the k >= 26 domain
+ *                          shards across the 8 GPUs"; zkb_comm_init first; COLLECTIVE).  n = P * M.  direction 0: in = this rank's
+ *                          cyclic subsequence x[rank + P t] (M elements), out = the strip layout (row k1 * M/P + t holds
+ *                          X[k1 M + rank M/P + t]); direction 1: strips in, cyclic out -- so forward (0) followed by the inverse root
+ *                          and 1/n scale (1) is a round trip with no re-layout.  The twiddle multiply and the all-to-all are fused
+ *                          into the store phase of the transform kernels: results go straight into the owner's window over NVLink
+ *                          peer memory (cudaIpc-mapped); ZKB_SHARDED_EXCHANGE=nccl selects the ncclSend/ncclRecv baseline.
+ * zkb_msm_g1_sharded_dev   point-range sharded MSM (aggregator/configs/compression_thin.config: 2^26 points over 8 GPUs): every rank
+ *                          reduces its own slice, the 64-byte partial sums are all-gathered and added; same result on every rank. */
+ZKB_API int32_t zkb_ntt_fr_sharded_dev(zkb_ctx *ctx, const uint64_t *in_dev, uint64_t *out_dev, uint32_t log_n, const uint64_t omega[4],
+                                       const uint64_t *scale /* HOST pointer or NULL */, int32_t direction, void *stream);
+ZKB_API int32_t zkb_msm_g1_sharded_dev(zkb_ctx *ctx, const uint64_t *scalars_shard_dev, const uint64_t *bases_shard_dev, uint64_t n_local,
+                                       uint64_t out_affine[8], uint8_t *out_compressed, void *stream);
+
 /* zkb_comm_*   NCCL communicator of a context for the multi-GPU create_proof (one process per GPU).  Rank 0 creates a
  * 128-byte unique id, the host layer broadcasts it, every rank calls zkb_comm_init.  With a communicator the proving session
  * stays replicated (identical transcript and proof bytes on every rank) while commitment batches (column i -> rank i mod P) and

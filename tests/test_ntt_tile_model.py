@@ -49,21 +49,21 @@ def test_fused_variants(log_n):
     sampled_check([v * s % M.R_MOD for v, s in zip(vals, ins)], out, w, ks)
 
 
-@pytest.mark.parametrize("log_n", [10, 11, 12, 13])
+@pytest.mark.parametrize("log_n", [11, 12, 13])
 def test_production_constants(log_n):
-    # the kernel's own limits (1024-element tiles, 128 threads, inner factors <= 2^8): single pass at 2^10, two passes (6,5) / (6,6) / (7,6) above
+    # the kernel's own limits (2048-element tiles, 256 threads, inner factors <= 2^9): single pass at 2^11, two passes (6,6) / (7,6) above
     rnd = random.Random(7 + log_n)
     n = 1 << log_n
     vals = [rnd.randrange(M.R_MOD) for _ in range(n)]
     w = M.omega_for(log_n)
-    out = M.ntt(vals, log_n, w, tile_bits=10, max_bits=10, threads=128, pref_inner_bits=8, max_inner_bits=9)
+    out = M.ntt(vals, log_n, w, tile_bits=11, max_bits=11, threads=256, pref_inner_bits=9, max_inner_bits=9)
     sampled_check(vals, out, w, [0, 1, n // 2, n - 1, rnd.randrange(n), rnd.randrange(n)])
 
 
 def test_plan_shapes_of_the_kernel_limits():
-    # 2^24 (BASELINE config #2) = 8 + 8 + 8; 2^20 = 7 + 7 + 6; 2^28 (largest Fr domain) = 9 + 9 + 10; inner factors <= 2^8 up to 2^26
-    shapes = {k: M.Plan(k, 10, 10, 8, 9).bits for k in range(0, 29)}
-    assert shapes[24] == [8, 8, 8] and shapes[20] == [7, 7, 6] and shapes[28] == [9, 9, 10] and shapes[10] == [10] and shapes[12] == [6, 6]
-    assert shapes[11] == [6, 5] and shapes[18] == [8, 10] and shapes[19] == [7, 6, 6] and shapes[26] == [8, 8, 10] and shapes[27] == [9, 9, 9]
+    # 2^24 (BASELINE config #2) = 8 + 8 + 8; 2^20 = 9 + 11; 2^28 (largest Fr domain) = 9 + 9 + 10; every inner factor <= 2^9
+    shapes = {k: M.Plan(k, 11, 11, 9, 9).bits for k in range(0, 29)}
+    assert shapes[24] == [8, 8, 8] and shapes[20] == [9, 11] and shapes[28] == [9, 9, 10] and shapes[11] == [11] and shapes[12] == [6, 6]
+    assert shapes[21] == [7, 7, 7] and shapes[26] == [9, 9, 8]
     for k, b in shapes.items():
-        assert sum(b) == k and all(x >= 5 for x in b) or len(b) == 1   # multi-pass factors >= 2^5: C * (A + 1) fits the padded tile
+        assert sum(b) == k and (len(b) == 1 or all(x >= 6 for x in b))   # multi-pass factors >= 2^6: C * (A + 1) fits the padded tile

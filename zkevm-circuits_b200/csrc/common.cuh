@@ -71,13 +71,18 @@ struct zkb_ctx {
     // multi-GPU: NCCL communicator of this rank (comm.cu); nranks == 1 -> everything local
     void *nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory exchange window of this rank (sharded.cu): cudaMalloc'ed, exported with cudaIpc, mapped by every other rank
+    void *win_local = nullptr;
+    size_t win_bytes = 0;
+    void *win_peers[16] = {nullptr};   // win_peers[rank] == win_local
+    std::map<std::array<uint64_t, 6>, void *> shard_tw;   // cached twiddle tables of the sharded transforms
     uint64_t launches = 0;
     bool ntt_ready = false;   // per-device kernel attributes / constants of ntt.cu are set (a context owns one device)
     uint64_t msm_last_adds = 0;
     uint32_t msm_last_levels = 0;   // reduction levels >= 1 the last MSM actually executed (device-side decision)
     std::map<std::array<uint64_t, 5>, zkb::NttPlan> ntt_plans;
     // grow-only scratch arenas (device), keyed by purpose; avoids cudaMalloc in steady state
-    zkb::DeviceBuffer scratch[12];
+    zkb::DeviceBuffer scratch[14];
     // cached device blocks (size -> pointers) recycled between proving sessions: cudaMalloc/cudaFree of tens of GB per proof
     // costs seconds and is wildly variable; blocks go back to the driver only at zkb_destroy
     std::multimap<size_t, void *> block_cache;
@@ -114,6 +119,17 @@ int32_t ntt_fr_device(zkb_ctx *ctx, const Fr *src, Fr *dst, uint32_t log_n, cons
 // `count` transforms in one launch per pass: column y reads h_src[y], writes h_dst[y] (HOST arrays of device pointers; may alias)
 int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_dst, uint32_t count, uint32_t log_n,
                             const Fr &omega, const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, cudaStream_t st);
+// final-pass routing of a domain-sharded transform: element i of the result is multiplied by out_tw[i] and stored into
+// peers[i >> log_blk] at offset (rank << log_blk) + (i mod 2^log_blk)   (peers: device pointers valid on this device, own window included)
+struct NttPeerRoute {
+    const Fr *out_tw;
+    bool routed;          // false: twiddle only, plain store (the NCCL all-to-all variant)
+    uint32_t log_blk, rank;
+    int nranks;
+    Fr *peers[16];
+};
+int32_t ntt_fr_batch_device_ex(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_dst, uint32_t count, uint32_t log_n, const Fr &omega,
+                               const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, const NttPeerRoute *route, cudaStream_t st);
 // synchronises: the result point is returned to the host
 int32_t msm_g1_device(zkb_ctx *ctx, const Fr *scalars, const G1Affine *bases, uint64_t n, G1Affine *out_affine_host, cudaStream_t st);
 // `batch` MSMs over the same bases in one pass (d_scalar_cols: DEVICE array of device pointers; batch <= msm_max_batch(n))
@@ -138,6 +154,14 @@ int32_t lincomb_device(zkb_ctx *ctx, const Fr *const *d_polys, const Fr *d_coefs
 int32_t batch_invert_device(zkb_ctx *ctx, const Fr *a, Fr *out, uint64_t n, cudaStream_t st);
 // in-place u64 sum across the context's ranks (exact gather when the supports are disjoint); no-op for a single rank
 int32_t comm_allreduce_u64(zkb_ctx *ctx, void *dev_buf, size_t count, cudaStream_t st);
+// all-gather: every rank contributes bytes_per_rank; recv holds nranks blocks in rank order (send may be recv + rank * bytes_per_rank)
+int32_t comm_allgather(zkb_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t st);
+// all-to-all: block s of `send` (bytes_per_block each) goes to rank s; block j of `recv` came from rank j
+int32_t comm_alltoall(zkb_ctx *ctx, const void *send, void *recv, size_t bytes_per_block, cudaStream_t st);
+// stream-ordered barrier across the ranks (a 8-byte all-reduce): work queued before it on every rank is complete when it completes
+int32_t comm_barrier(zkb_ctx *ctx, cudaStream_t st);
+// peer-memory window of at least `bytes` on every rank, mapped into every rank (cudaIpc); COLLECTIVE, same `bytes` everywhere
+int32_t comm_window(zkb_ctx *ctx, size_t bytes, cudaStream_t st);
 
 struct DevPool {  // owns device allocations of a pk / session; blocks are recycled through the context's block cache
     zkb_ctx *ctx = nullptr;
@@ -156,5 +180,5 @@ struct DevPool {  // owns device allocations of a pk / session; blocks are recyc
     int32_t fr(uint64_t n, Fr **out) { return alloc(n * sizeof(Fr), (void **)out); }
 };
 
-enum ScratchSlot { SCR_NTT = 0, SCR_MSM_A = 1, SCR_MSM_B = 2, SCR_MSM_C = 3, SCR_HOSTIO_A = 4, SCR_HOSTIO_B = 5, SCR_MISC = 6, SCR_MISC2 = 7, SCR_MSM_TBL = 8, SCR_COMM = 9, SCR_NTT_DESC = 10, SCR_MSM_D = 11 };
+enum ScratchSlot { SCR_NTT = 0, SCR_MSM_A = 1, SCR_MSM_B = 2, SCR_MSM_C = 3, SCR_HOSTIO_A = 4, SCR_HOSTIO_B = 5, SCR_MISC = 6, SCR_MISC2 = 7, SCR_MSM_TBL = 8, SCR_COMM = 9, SCR_NTT_DESC = 10, SCR_MSM_D = 11, SCR_COMM_FLAG = 12, SCR_SHARD = 13 };
 }  // namespace zkb

@@ -5,21 +5,20 @@
 // extended_to_coeff}).  Same contract: in place, natural order in / natural order out, a'[k] = sum_j a[j] w^(jk).
 //
 // B200 design (NOT upstream's bit-reverse + log n global layers):
-//   n = A1 * A2 (* A3): 1 pass up to 2^10, 2 passes up to 2^18, 3 passes above (non-final factors <= 2^8, final <= 2^10; 2^9 from
-//   2^27).  A pass is ONE persistent kernel, FOUR 128-thread CTAs per SM, each walking over TILES of 1024 elements (32 KB): a tile
-//   is C = 1024 / A adjacent columns of the Cooley-Tukey index split, i.e. C independent length-A transforms whose rows are C*32
-//   contiguous bytes in HBM.  The four resident CTAs run out of phase, so while one waits for TMA data, converts layouts or
-//   streams results out, the others are in their multiplier-bound butterfly rounds: the integer-multiply pipe (the bound, see
-//   DESIGN.md) stays fed.  Per tile:
+//   n = A1 * A2 (* A3): 1 pass up to 2^11, 2 passes up to 2^20, 3 passes above (non-final factors <= 2^9, final <= 2^11).  A pass
+//   is ONE persistent kernel, TWO 256-thread CTAs per SM, each walking over TILES of 2048 elements (64 KB): a tile is C = 2048 / A
+//   adjacent columns of the Cooley-Tukey index split, i.e. C independent length-A transforms whose rows are C*32 contiguous bytes
+//   in HBM.  The two resident CTAs run out of phase, so while one waits for TMA data, converts layouts or streams results out, the
+//   other is in its multiplier-bound butterfly rounds: the integer-multiply pipe (the bound) stays fed.  Per tile:
 //     * the data tile is fetched by TMA (cp.async.bulk.tensor.2d through a per-column tensor map: box = 256 rows x 32 B;
 //       the contiguous sub-transforms of the last pass by cp.async.bulk), completion signalled on an mbarrier
 //       (complete_tx::bytes); the fetch of tile i+1 is issued the moment tile i's last result left shared memory;
 //     * the tile's inter-pass twiddles w_n^(j_in * k) are TMA-staged as well: the table is stored tile-major in the order the
-//       store phase consumes it and streams through a ring of four 4 KB slots (one slot = the 128 elements of one store
+//       store phase consumes it and streams through a ring of four 8 KB slots (one slot = the 256 elements of one store
 //       iteration), refilled four iterations ahead -- across the tile boundary, so the next tile's first twiddles are already
 //       resident while its butterflies run;
 //     * the A/2 local twiddles of the pass sit in shared memory for the life of the CTA (one bulk copy at kernel start);
-//     * decimation in frequency in radix-8 rounds held in registers (8 elements / thread / round, 128 threads), the short round
+//     * decimation in frequency in radix-8 rounds held in registers (8 elements / thread / round, 256 threads), the short round
 //       first and a radix-8 round last, where the unit twiddles (3 of 8 per thread, plus the whole last stage) are known at
 //       compile time and cost no multiply: (A/2) log2 A - (A - 1) + A/8 multiplies per transform instead of (A/2) log2 A;
 //     * two 16-byte planes with an XOR swizzle + one padding slot per column -> conflict-free 128-bit LDS/STS;
@@ -33,16 +32,19 @@
 
 namespace zkb {
 
-constexpr int NTT_TILE_BITS = 10;        // 1024 elements = 32 KB per tile
-constexpr int NTT_MAX_BITS = 10;         // largest in-CTA transform (final pass: no twiddle ring in shared memory)
-constexpr int NTT_PREF_INNER_BITS = 8;   // non-final passes: 4 KB of local twiddles next to the 16 KB twiddle ring -> four CTAs per SM
-constexpr int NTT_MAX_INNER_BITS = 9;    // only for log_n >= 27 (8 KB of local twiddles: three resident CTAs)
-constexpr int NTT_THREADS = 128;         // 8 elements per thread and round
-constexpr int NTT_CTAS_PER_SM = 4;
+// Measured on B200 (profiles/r02_ntt_tile_v5*_ncu.txt): two 256-thread CTAs per SM on 2048-element tiles reach 70 % of the
+// integer-multiply pipe; four 128-thread CTAs on 1024-element tiles do NOT do better (69 %): the four instruction streams of a
+// 440 KB kernel start to miss the instruction cache (stall_no_instruction 13 % of the samples vs 2 %).
+constexpr int NTT_TILE_BITS = 11;        // 2048 elements = 64 KB per tile
+constexpr int NTT_MAX_BITS = 11;         // largest in-CTA transform (final pass: no twiddle ring in shared memory)
+constexpr int NTT_PREF_INNER_BITS = 9;   // non-final passes: <= 8 KB of local twiddles next to the 32 KB twiddle ring -> two CTAs per SM
+constexpr int NTT_MAX_INNER_BITS = 9;
+constexpr int NTT_THREADS = 256;         // 8 elements per thread and round
+constexpr int NTT_CTAS_PER_SM = 2;
 constexpr int TW_LO_BITS = 12;
 constexpr uint32_t NTT_BOX_ROWS = 256;
 constexpr uint32_t NTT_HDR_BYTES = 128;                                  // mbarriers: [0] data, [1] local twiddles, [2..5] ring slots
-constexpr uint32_t NTT_DBUF_BYTES = 32u * ((1u << NTT_TILE_BITS) + 32u);  // two 16-byte planes of C*(A+1) <= 1024+32 slots (A >= 32 in multi-pass plans)
+constexpr uint32_t NTT_DBUF_BYTES = 32u * ((1u << NTT_TILE_BITS) + 32u);  // two 16-byte planes of C*(A+1) <= 2048+32 slots (A >= 64 in multi-pass plans)
 constexpr uint32_t NTT_TW_SLOTS = 4;
 constexpr uint32_t NTT_TW_SLOT_ELEMS = NTT_THREADS;                       // one store iteration
 constexpr uint32_t NTT_TW_RING_BYTES = NTT_TW_SLOTS * NTT_TW_SLOT_ELEMS * 32u;
@@ -66,6 +68,12 @@ struct PassArgs {
     const Fr *tw;        // inter-pass table of this boundary, tile-major (non-final passes)
     const Fr *scale;
     const Fr *in_scale;  // optional per-element input multiplier (first pass only): coset scaling tables
+    // final pass of a domain-sharded transform (sharded.cu): output element oidx is multiplied by out_tw[oidx] and stored into the
+    // receive window of rank (oidx >> peer_log_blk) at row peer_rank -- the all-to-all of the four-step NTT happens inside the
+    // store phase, over NVLink peer memory, tile by tile
+    const Fr *out_tw;
+    uint32_t peer_routed, peer_log_blk, peer_rank;
+    Fr *peers[16];
     const CUtensorMap *maps;   // per column: 2-D view [n / S rows][S * 4 u64] of the pass input (non-final passes)
     const Fr *const *src;      // per column input  (final pass: bulk copies)
     Fr *const *dst;            // per column output
@@ -359,7 +367,12 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_CTAS_PER_SM) ntt_tile_kernel(
                         const uint32_t m = (uint32_t)(oidx % 3);
                         if (m) v = fp_mul(v, zeta_pow(3 - m));  // ZETA^(-m) = ZETA^(3-m)
                     }
-                    fp_store_stream(out + oidx, v);
+                    if (p.out_tw) v = fp_mul(v, fp_load(p.out_tw + oidx));   // sharded transform: omega^(rank * k2)
+                    if (p.peer_routed) {   // ... and straight into the owner's window (peer store over NVLink)
+                        Fr *w = p.peers[oidx >> p.peer_log_blk];
+                        fp_store_stream(w + ((uint64_t)p.peer_rank << p.peer_log_blk) + (oidx & ((1ull << p.peer_log_blk) - 1)), v);
+                    } else
+                        fp_store_stream(out + oidx, v);
                 }
             }
             fence_proxy_async();
@@ -532,15 +545,22 @@ static uint32_t pass_smem_bytes(const PassGeom &g) {
 
 // batch of `count` transforms: column y reads h_src[y], writes h_dst[y] (HOST arrays of device pointers; the arrays may alias,
 // h_src[y] == h_dst[y] is an in-place transform).
+int32_t ntt_fr_batch_device_ex(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_dst, uint32_t count, uint32_t log_n, const Fr &omega,
+                               const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, const NttPeerRoute *route, cudaStream_t st);
 int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_dst, uint32_t count, uint32_t log_n, const Fr &omega,
                             const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, cudaStream_t st) {
+    return ntt_fr_batch_device_ex(ctx, h_src, h_dst, count, log_n, omega, scale_host, coset_zeta, d_in_scale, nullptr, st);
+}
+int32_t ntt_fr_batch_device_ex(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_dst, uint32_t count, uint32_t log_n, const Fr &omega,
+                               const Fr *scale_host, int coset_zeta, const Fr *d_in_scale, const NttPeerRoute *route, cudaStream_t st) {
+    ZKB_ARG(route == nullptr || (count == 1 && route->out_tw && route->nranks >= 1 && route->nranks <= 16));
     ZKB_ARG(log_n <= 28 && count >= 1 && h_src && h_dst);
     ZKB_ARG(coset_zeta >= 0 && coset_zeta <= 2);
     NttPlan *plan = nullptr;
     ZKB_TRY(get_plan(ctx, log_n, omega, &plan));
     if (!ctx->ntt_ready) {
         // per device (a context owns one device): opt in to the large dynamic shared-memory window, upload ZETA
-        // four CTAs per SM: header + data tile + twiddle ring + 4 (8) KB of local twiddles (non-final) or <= 16 KB (final, no ring)
+        // two CTAs per SM: header + data tile + twiddle ring + <= 8 KB of local twiddles (non-final) or <= 32 KB (final, no ring)
         ZKB_CUDA(cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(NTT_HDR_BYTES + NTT_DBUF_BYTES + NTT_TW_RING_BYTES + (32u << (NTT_MAX_INNER_BITS - 1)))));
         ZKB_CUDA(cudaFuncSetAttribute(ntt_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -626,6 +646,13 @@ int32_t ntt_fr_batch_device(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *h_d
         p.tw = g.is_final ? nullptr : (ps == npass - 2 ? last_tw : plan->tw_b[ps]);
         p.scale = d_scale;
         p.in_scale = d_in_scale;
+        if (route && g.is_final) {
+            p.out_tw = route->out_tw;
+            p.peer_routed = route->routed ? 1u : 0u;
+            p.peer_log_blk = route->log_blk;
+            p.peer_rank = route->rank;
+            for (int i = 0; i < route->nranks; ++i) p.peers[i] = route->peers[i];
+        }
         p.maps = (const CUtensorMap *)(dblob + (size_t)ps * count * sizeof(CUtensorMap));
         p.src = (const Fr *const *)(dblob + maps_bytes + (size_t)(2 * ps) * tbl_bytes);
         p.dst = (Fr *const *)(dblob + maps_bytes + (size_t)(2 * ps + 1) * tbl_bytes);

@@ -106,7 +106,7 @@ __global__ void mul_arrays_kernel(const Fr *__restrict__ a, const Fr *__restrict
 }
 // out[i] -= low[i] for i < k (subtract a low-degree polynomial given on the device)
 __global__ void sub_low_kernel(Fr *__restrict__ out, const Fr *__restrict__ low, uint32_t k) {
-    uint32_t i = threadIdx.x;
+    uint32_t i = threadIdx.x;   // one block of 256 threads: a rotation set has at most 256 points
     if (i < k) fp_store(out + i, fp_sub(fp_load(out + i), fp_load(low + i)));
 }
 
@@ -1494,7 +1494,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     ZKB_TRY(pool.fr(n, &hx));
     ZKB_TRY(pool.fr(n, &work));
     ZKB_TRY(pool.fr(n, &work2));
-    ZKB_TRY(pool.fr(64, &d_small));
+    ZKB_TRY(pool.fr(256, &d_small));
     ZKB_CUDA(cudaMemsetAsync(hx, 0, n * sizeof(Fr), st));
     struct SetData { std::vector<Fr> pts; std::vector<std::vector<Fr>> r_coeffs; };
     std::vector<SetData> sdata(rsets.size());
@@ -1504,7 +1504,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
             RSet &rs = rsets[si];
             SetData &sd = sdata[si];
             for (int64_t r : rs.rots) sd.pts.push_back(point_of[r]);
-            ZKB_ARG(sd.pts.size() <= 32);
+            ZKB_ARG(sd.pts.size() <= 256);   // Keccak's hot cell column is opened at 56 rotations (keccak_packed_multi.rs:59-68)
             // N_i(X) = sum_j y^j (P_ij(X) - R_ij(X))
             std::vector<Fr *> ptrs;
             std::vector<Fr> cf;
@@ -1526,7 +1526,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
             ZKB_CUDA(cudaMemcpyAsync(d_c, cf.data(), cf.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
             ZKB_TRY(lincomb_device(ctx, d_p, d_c, (uint32_t)ptrs.size(), n, work, false, st));
             ZKB_CUDA(cudaMemcpyAsync(d_small, rsum.data(), rsum.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
-            sub_low_kernel<<<1, 32, 0, st>>>(work, d_small, (uint32_t)rsum.size());
+            sub_low_kernel<<<1, 256, 0, st>>>(work, d_small, (uint32_t)rsum.size());
             ctx->launches++;
             ZKB_CUDA(cudaStreamSynchronize(st));
             // divide by the vanishing polynomial of the set, one root at a time
@@ -1592,7 +1592,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_CUDA(cudaMemcpyAsync(d_c, cf.data(), cf.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
         ZKB_TRY(lincomb_device(ctx, d_p, d_c, (uint32_t)ptrs.size(), n, work, false, st));
         ZKB_CUDA(cudaMemcpyAsync(d_small, &const_term, sizeof(Fr), cudaMemcpyHostToDevice, st));
-        sub_low_kernel<<<1, 32, 0, st>>>(work, d_small, 1);
+        sub_low_kernel<<<1, 256, 0, st>>>(work, d_small, 1);
         ctx->launches++;
         ZKB_CUDA(cudaStreamSynchronize(st));
         ZKB_TRY(kate_division_device(ctx, work, n, su, work2, st));

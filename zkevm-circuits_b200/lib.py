@@ -60,6 +60,8 @@ SIGNATURES = {
     "zkb_kate_division_dev": (ctypes.c_int32, [_vp, _vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "zkb_ntt_cross_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint64, _vp, _vp]),
     "zkb_g1_sum_affine_host": (ctypes.c_int32, [_vp, ctypes.c_uint64, _vp, _vp]),
+    "zkb_ntt_fr_sharded_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint32, _vp, _vp, ctypes.c_int32, _vp]),
+    "zkb_msm_g1_sharded_dev": (ctypes.c_int32, [_vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "zkb_comm_unique_id": (ctypes.c_int32, [_vp]),
     "zkb_comm_init": (ctypes.c_int32, [_vp, _vp, ctypes.c_int32, ctypes.c_int32]),
     "zkb_comm_destroy": (ctypes.c_int32, [_vp]),

@@ -141,3 +141,32 @@ def strips_to_natural(strips, world):
         for k in range(world):
             out[k * M + s * blk: k * M + (s + 1) * blk] = st[k * blk:(k + 1) * blk]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- C-ABI sharded entry points
+def ntt_sharded_dev(local, log_n, omega, direction=0, scale=None, ctx=None):
+    """zkb_ntt_fr_sharded_dev: one size-2^log_n transform over the ranks of the context's communicator (Context.init_comm first).
+    direction 0: `local` = x[rank + P t] (cyclic) -> strips;  direction 1: strips -> cyclic.  The twiddle + all-to-all run inside the
+    transform kernels over NVLink peer memory (ZKB_SHARDED_EXCHANGE=nccl: ncclSend/ncclRecv baseline).  Returns a new tensor."""
+    import torch
+    from .lib import default_context
+    from .arithmetic import _cur_stream
+    ctx = ctx or default_context()
+    out = torch.empty_like(local)
+    w = np.ascontiguousarray(omega, dtype=np.uint64)
+    sc = np.ascontiguousarray(scale, dtype=np.uint64) if scale is not None else None
+    check(ctx.lib.zkb_ntt_fr_sharded_dev(ctx.handle, _vp(local.data_ptr()), _vp(out.data_ptr()), int(log_n), _vp(w.ctypes.data),
+                                         _vp(sc.ctypes.data) if sc is not None else None, int(direction), _cur_stream()))
+    return out
+
+
+def msm_sharded_dev(coeffs_shard, bases_shard, ctx=None):
+    """zkb_msm_g1_sharded_dev: point-range sharded MSM -> (affine uint64[8], compressed bytes), identical on every rank."""
+    from .lib import default_context
+    from .arithmetic import _cur_stream
+    ctx = ctx or default_context()
+    out = np.zeros(8, dtype=np.uint64)
+    comp = (ctypes.c_uint8 * 32)()
+    check(ctx.lib.zkb_msm_g1_sharded_dev(ctx.handle, _vp(coeffs_shard.data_ptr()), _vp(bases_shard.data_ptr()), int(coeffs_shard.shape[0]),
+                                         _vp(out.ctypes.data), ctypes.cast(comp, _vp), _cur_stream()))
+    return out, bytes(comp)
