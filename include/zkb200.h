@@ -50,6 +50,10 @@ ZKB_API uint32_t zkb_version(void);
 /* Number of kernel launches issued through this context so far (bench.py's `gpu_launches`). */
 ZKB_API uint64_t zkb_launch_count(const zkb_ctx *ctx);
 ZKB_API int32_t zkb_sync(zkb_ctx *ctx);
+/* Device time per kernel class, measured with CUDA event pairs on the launching stream (off by default).  cls: 0 ntt_tile_kernel,
+ * 1 msm_acc_chunk_kernel, 2 expr_kernel.  zkb_prof_read synchronises on the recorded events; reset != 0 clears the counters. */
+ZKB_API int32_t zkb_prof_enable(zkb_ctx *ctx, int32_t on);
+ZKB_API int32_t zkb_prof_read(zkb_ctx *ctx, int32_t cls, uint64_t *launches, double *ms, int32_t reset);
 /* Stream the context launches on (cudaStream_t as void*), for event timing by the caller. */
 ZKB_API void *zkb_stream(zkb_ctx *ctx);
 

@@ -9,13 +9,14 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
 
 
-def run(sizes=(16, 22, 24), msm_log=20, reps=3):
+def run(sizes=(16, 22, 24), msm_log=20, reps=3, ctx=None):
     rank, world = dist.get_rank(), dist.get_world_size()
     import zkb200
     from zkb200 import arithmetic as A, parallel
     from zkb200.params import g1_generator
-    ctx = zkb200.default_context(torch.cuda.current_device())
-    ctx.init_comm()
+    if ctx is None:
+        ctx = zkb200.default_context(torch.cuda.current_device())
+        ctx.init_comm()
     out = {"world": world}
 
     def timed(fn):

@@ -24,10 +24,67 @@ row a10 of SURVEY 8a, and stay on the CPU).  This module is test / benchmark inf
 """
 import numpy as np
 
-from zkb200 import arithmetic as A
-from zkb200 import poly
 from zkb200.plonk import ConstraintSystem, Expression as E, ADVICE, FIXED, INSTANCE, NEG, ADD, MUL, SCALED, CONST, CHALLENGE
-from zkb200.params import fr_scalar_dev, fr_ints_to_dev, bcast, fr_pow2k_dev
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+ROOT_OF_UNITY_28 = 0x03DDB9F5166D18B798865EA93DD31F743215CF6DD39329C8D34F1ED960C37C9C
+
+
+def bcast(scalar_t, n):
+    return scalar_t.expand(n, 4).contiguous()
+
+
+class DeviceOps:
+    """witness arithmetic on the GPU through the product's element-wise field kernels (tests and the GPU arm of bench.py)"""
+    device = "cuda"
+
+    def __init__(self):
+        from zkb200 import arithmetic as A, poly, params
+        self.A, self.poly, self.params = A, poly, params
+
+    def rand(self, n, seed): return self.A.random_fr_dev(n, seed)
+    def from_ints(self, v): return self.params.fr_ints_to_dev(v)
+    def scalar(self, v): return self.params.fr_scalar_dev(v % R_MOD)
+    def mul(self, a, b): return self.A.field_binop_dev(self.A.FR, self.A.OP_MUL, a, b)
+    def add(self, a, b): return self.A.field_binop_dev(self.A.FR, self.A.OP_ADD, a, b)
+    def powers(self, base_int, n): return self.poly.fr_powers_dev(self.scalar(base_int).cpu().numpy().view(np.uint64)[0], n)
+
+
+class OracleOps:
+    """the same arithmetic on the CPU through the oracle library: used by bench.py's reference arm, where nothing of the product
+    may run (values differ from DeviceOps' generator; only the shape matters there)"""
+    device = "cpu"
+
+    def __init__(self):
+        import oracle_lib
+        self.o = oracle_lib.load()
+
+    @staticmethod
+    def _np(t): return np.ascontiguousarray(t.numpy()).view(np.uint64)
+    @staticmethod
+    def _t(a):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
+
+    def rand(self, n, seed):
+        rng = np.random.default_rng(seed)
+        a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        a[:, 3] = rng.integers(0, 0x30644E72E131A029, size=n, dtype=np.uint64)
+        return self._t(a)
+
+    def from_ints(self, v):
+        z = np.zeros((v.shape[0], 4), dtype=np.uint64)
+        z[:, 0] = v.numpy().astype(np.uint64)
+        return self._t(self.o.fr_from_canonical(z))
+
+    def scalar(self, v):
+        v %= R_MOD
+        z = np.array([[(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]], dtype=np.uint64)
+        return self._t(self.o.fr_from_canonical(z))
+
+    def mul(self, a, b): return self._t(self.o.fr_mul(self._np(a), self._np(b)))
+    def add(self, a, b): return self._t(self.o.fr_add(self._np(a), self._np(b)))
+    def powers(self, base_int, n): return self._t(self.o.fr_powers(self._np(self.scalar(base_int))[0], n))
 
 KECCAK_TABLE_ROWS = (59049, 65536, 46656, 78125, 59049)  # normalize_3, normalize_4, normalize_6, chi_base, (second normalize_3 use)
 
@@ -50,8 +107,10 @@ class _Lcg:
 
 class ShapedCircuit:
     def __init__(self, k, *, n_base=8, n_defined=8, n_gates=32, hot_rots=(0, 1, -1, 2), cold_rots=(0, 1, -1, 2), table_rows=(), table_width=2,
-                 n_lookup_args=0, pairs_per_table=2, lookup_rots=(0, 1, 2), n_perm=9, phases=2, instance_cells=0, seed=1):
+                 n_lookup_args=0, pairs_per_table=2, lookup_rots=(0, 1, 2), n_perm=9, phases=2, instance_cells=0, seed=1, ops=None):
         import torch
+        ops = ops or DeviceOps()
+        self.ops = ops
         assert 1 <= phases <= 3 and n_defined >= 1 and n_base >= 3
         self.k, self.n = k, 1 << k
         n = self.n
@@ -162,11 +221,11 @@ class ShapedCircuit:
         usable = n - (bf + 1)
         self.usable = usable
         assert usable > max(table_rows, default=0), "the largest table does not fit the usable rows"
-        # ---- values (device)
-        dev = "cuda"
+        # ---- values (on ops.device)
+        dev = ops.device
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed)
-        one = fr_scalar_dev(1)
+        one = ops.scalar(1)
         zero4 = torch.zeros((n, 4), dtype=torch.int64, device=dev)
         rows = torch.arange(n, device=dev)
         is_usable = rows < usable
@@ -180,17 +239,16 @@ class ShapedCircuit:
             for cc in range(W):
                 v = torch.where(rows < table_rows[t], rows * (7 * cc + 1) + cc * (rows > 0), torch.zeros_like(rows))  # row 0 = all zeros
                 cols_t.append(v)
-                self.fixed.append(fr_ints_to_dev(v))
+                self.fixed.append(ops.from_ints(v))
             tbl_int.append(cols_t)
 
         def blind(col, s):
-            col[usable:] = A.random_fr_dev(bf + 1, seed * 1000 + s)
+            col[usable:] = ops.rand(bf + 1, seed * 1000 + s)
             return col
-        mul = lambda a, b: A.field_binop_dev(A.FR, A.OP_MUL, a, b)
-        add = lambda a, b: A.field_binop_dev(A.FR, A.OP_ADD, a, b)
+        mul, add = ops.mul, ops.add
         adv = [None] * na
         for c in range(n_base):
-            adv[c] = A.random_fr_dev(n, seed * 7919 + c)
+            adv[c] = ops.rand(n, seed * 7919 + c)
         for s, (x, r, y, z) in enumerate(defs):
             xr = torch.roll(adv[x], -r, dims=0).contiguous() if r else adv[x]
             adv[c_def0 + s] = blind(add(mul(xr, adv[y]), adv[z]), 10 + s)
@@ -198,10 +256,10 @@ class ShapedCircuit:
             t = pr // pairs_per_table
             idx = torch.randint(0, table_rows[t], (n,), device=dev, generator=gen)
             for cc in range(W):
-                adv[c_pair0 + pr * W + cc] = blind(fr_ints_to_dev(tbl_int[t][cc][idx]), 5000 + pr * W + cc)
+                adv[c_pair0 + pr * W + cc] = blind(ops.from_ints(tbl_int[t][cc][idx]), 5000 + pr * W + cc)
         # copy columns: c_j[r] = c_0[pi_j(r)] on usable rows; sigma links the cells holding the same c_0 cell in a cycle
         Pn = n_perm
-        base = A.random_fr_dev(n, seed * 7 + 3)
+        base = ops.rand(n, seed * 7 + 3)
         pis = [torch.arange(usable, device=dev)] + [torch.randperm(usable, device=dev, generator=gen) for _ in range(Pn - 1)]
         for j in range(Pn):
             col = base.clone()
@@ -210,15 +268,14 @@ class ShapedCircuit:
         self.instances = []
         if instance_cells:
             vals = torch.randint(0, 256, (instance_cells,), device=dev, generator=gen)
-            inst = fr_ints_to_dev(vals)
+            inst = ops.from_ints(vals)
             self.instances = [inst]
-            col = A.random_fr_dev(n, seed * 7 + 11)
+            col = ops.rand(n, seed * 7 + 11)
             col[:instance_cells] = inst
             adv[c_pi] = blind(col, 300)
         self.adv0 = adv
-        omega, _ = A.root_of_unity(k)
-        Wp = poly.fr_powers_dev(omega, n)
-        delta = fr_pow2k_dev(fr_scalar_dev(7), 28)
+        Wp = ops.powers(pow(ROOT_OF_UNITY_28, 1 << (28 - k), R_MOD), n)   # omega_k^i
+        delta = ops.scalar(pow(7, 1 << 28, R_MOD))                      # DELTA = 7^(2^28)
         dpow = [one]
         for _ in range(len(perm_columns)): dpow.append(mul(dpow[-1], delta))
         invs = []
@@ -237,10 +294,10 @@ class ShapedCircuit:
             self.sigma.append(mul(Wp, bcast(dpow[Pn], n)))
         nsets = (len(perm_columns) + (degree - 2) - 1) // (degree - 2)
         self.nsets = nsets
-        self.z_blinds = A.random_fr_dev(max(1, nsets * bf), seed * 7 + 4)[: nsets * bf]
-        self.phi_blinds = A.random_fr_dev(max(1, L * bf), seed * 7 + 5)[: L * bf]
-        self.random_poly = A.random_fr_dev(n, seed * 7 + 6)
-        self.transcript_repr = A.random_fr_dev(1, seed * 7 + 7)[0]
+        self.z_blinds = ops.rand(max(1, nsets * bf), seed * 7 + 4)[: nsets * bf]
+        self.phi_blinds = ops.rand(max(1, L * bf), seed * 7 + 5)[: L * bf]
+        self.random_poly = ops.rand(n, seed * 7 + 6)
+        self.transcript_repr = ops.rand(1, seed * 7 + 7)[0]
         self.shape = {"k": k, "advice_columns": na, "fixed_columns": nf, "instance_columns": 1 if instance_cells else 0, "phases": phases,
                       "gates": len(gates), "lookup_arguments": L, "lookup_input_sets": 3 * L, "lookup_tables": [int(x) for x in table_rows],
                       "lookup_width": W, "permutation_columns": len(perm_columns), "cs_degree": degree, "blinding_factors": bf,
@@ -249,20 +306,21 @@ class ShapedCircuit:
     def synthesize_dev(self, phase, challenges):
         """-> {advice column: device tensor} for the columns of `phase` (challenges: {idx: numpy uint64[4]})."""
         import torch
-        mul = lambda a, b: A.field_binop_dev(A.FR, A.OP_MUL, a, b)
+        ops = self.ops
+        mul = ops.mul
         out = {}
-        chd = lambda i: bcast(torch.from_numpy(np.ascontiguousarray(challenges[i]).view(np.int64)).cuda().reshape(1, 4), self.n)
+        chd = lambda i: bcast(torch.from_numpy(np.ascontiguousarray(challenges[i]).view(np.int64)).to(ops.device).reshape(1, 4), self.n)
         if phase == 0:
             for c, a in enumerate(self.adv0):
                 if a is not None: out[c] = a
         elif phase == 1:
             v = mul(mul(self.adv0[0], self.adv0[1]), chd(0))
-            v[self.usable:] = A.random_fr_dev(self.bf + 1, self.seed * 1000 + 999)
+            v[self.usable:] = ops.rand(self.bf + 1, self.seed * 1000 + 999)
             self._f = v
             out[self.c_f] = v
         elif phase == 2:
-            v = A.field_binop_dev(A.FR, A.OP_ADD, mul(self._f, chd(1)), self.adv0[2])
-            v[self.usable:] = A.random_fr_dev(self.bf + 1, self.seed * 1000 + 998)
+            v = ops.add(mul(self._f, chd(1)), self.adv0[2])
+            v[self.usable:] = ops.rand(self.bf + 1, self.seed * 1000 + 998)
             out[self.c_g] = v
         return out
 
@@ -270,7 +328,7 @@ class ShapedCircuit:
         return t.cpu().numpy().view(np.uint64)
 
 
-def keccak_shape(k=17, seed=3, scale=1.0):
+def keccak_shape(k=17, seed=3, scale=1.0, ops=None):
     """KeccakCircuit-like shape; `scale` < 1 shrinks the counts (not the rotation set) for the oracle-sized parity tests."""
     rots56 = tuple(range(-48, 8))                        # 56 distinct rotations on the hot column -> 58 blinding factors (59 unusable rows)
     tables = KECCAK_TABLE_ROWS if k >= 17 else tuple(min(r, (1 << k) // 3) for r in KECCAK_TABLE_ROWS)
@@ -278,13 +336,13 @@ def keccak_shape(k=17, seed=3, scale=1.0):
     n_def = sc(40, 3)
     return ShapedCircuit(k, n_base=sc(24, 4), n_defined=n_def, n_gates=max(sc(220, 60), n_def + 64), hot_rots=rots56, cold_rots=(0, 1, -12, 2, -1, 5, -24, 7),
                          table_rows=tables, table_width=2, n_lookup_args=sc(35, 5), pairs_per_table=sc(4, 2), lookup_rots=(0, 1, 2, 11, 12, -12),
-                         n_perm=sc(12, 8), phases=2, instance_cells=0, seed=seed)
+                         n_perm=sc(12, 8), phases=2, instance_cells=0, seed=seed, ops=ops)
 
 
-def super_shape(k=20, advice=256, seed=5, scale=1.0, n_gates=None):
+def super_shape(k=20, advice=256, seed=5, scale=1.0, n_gates=None, ops=None):
     """SuperCircuit-like shape with about `advice` advice columns, three phases, an instance column of 32 byte cells."""
     sc = lambda v, lo: max(lo, int(round(v * scale)))
-    tables = (256, 65536, 1 << 12, 50000) if k >= 17 else (256, (1 << k) // 3, (1 << k) // 5, (1 << k) // 4)
+    tables = (256, 65536, 1 << 12, 50000) if k >= 17 else (min(256, (1 << k) // 4), (1 << k) // 3, (1 << k) // 5, (1 << k) // 4)
     n_perm = sc(max(16, advice * 3 // 8), 9)
     pairs = sc(max(2, advice // 32), 2)
     width = 2
@@ -295,4 +353,4 @@ def super_shape(k=20, advice=256, seed=5, scale=1.0, n_gates=None):
     ng = n_gates if n_gates is not None else sc(max(256, advice * 5), 80)
     return ShapedCircuit(k, n_base=n_base, n_defined=n_def, n_gates=ng, hot_rots=(0, 1, -1, 2, 3, -2), cold_rots=(0, 1, -1, 2),
                          table_rows=tables, table_width=width, n_lookup_args=sc(max(8, advice // 8), 4), pairs_per_table=pairs,
-                         lookup_rots=(0, 1, -1), n_perm=n_perm, phases=3, instance_cells=32, seed=seed)
+                         lookup_rots=(0, 1, -1), n_perm=n_perm, phases=3, instance_cells=32, seed=seed, ops=ops)

@@ -77,6 +77,14 @@ struct zkb_ctx {
     void *win_peers[16] = {nullptr};   // win_peers[rank] == win_local
     std::map<std::array<uint64_t, 6>, void *> shard_tw;   // cached twiddle tables of the sharded transforms
     uint64_t launches = 0;
+    // optional per-kernel-class timing (zkb_prof_*): CUDA event pairs around the launches of the three hot kernels, on the
+    // launching stream; off by default (two event records per launch when on)
+    bool prof_on = false;
+    struct ProfPair { cudaEvent_t a, b; int cls; };
+    std::vector<ProfPair> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[4] = {0, 0, 0, 0};
+    uint64_t prof_count[4] = {0, 0, 0, 0};
     bool ntt_ready = false;   // per-device kernel attributes / constants of ntt.cu are set (a context owns one device)
     uint64_t msm_last_adds = 0;
     uint32_t msm_last_levels = 0;   // reduction levels >= 1 the last MSM actually executed (device-side decision)
@@ -109,6 +117,25 @@ int32_t scratch_get(zkb_ctx *ctx, int slot, size_t bytes, void **out);
 int32_t block_alloc(zkb_ctx *ctx, size_t bytes, void **out, size_t *got);
 void block_free(zkb_ctx *ctx, void *p, size_t bytes);
 inline cudaStream_t pick_stream(zkb_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+// kernel classes of zkb_prof_read: 0 ntt_tile_kernel, 1 msm_acc_chunk_kernel, 2 expr_kernel (quotient / lookup interpreter)
+enum ProfClass { PROF_NTT = 0, PROF_MSM_ACC = 1, PROF_EXPR = 2, PROF_OTHER = 3 };
+struct ProfScope {   // records an event pair around the launches issued while it is alive (no-op unless profiling is on)
+    zkb_ctx *ctx;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int cls;
+    ProfScope(zkb_ctx *c, int cl, cudaStream_t s) : ctx(c), st(s), cls(cl) {
+        if (!ctx->prof_on) return;
+        auto get = [&]() { cudaEvent_t e = nullptr; if (!ctx->prof_free.empty()) { e = ctx->prof_free.back(); ctx->prof_free.pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        ctx->prof_pending.push_back({a, b, cls});
+    }
+};
 
 // ---- cross-translation-unit device-side services (all launch on `st`, none synchronises unless stated) ----------------
 Fr host_root_of_unity(uint32_t k);

@@ -116,6 +116,8 @@ extern "C" int32_t zkb_destroy(zkb_ctx *ctx) {
         for (int i = 0; i < 3; ++i)
             if (p.loc[i]) cudaFree(p.loc[i]);
     }
+    for (auto &pp : ctx->prof_pending) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
     for (auto &b : ctx->scratch)
         if (b.ptr) cudaFree(b.ptr);
     for (auto &kv : ctx->block_cache) cudaFree(kv.second);
@@ -123,6 +125,31 @@ extern "C" int32_t zkb_destroy(zkb_ctx *ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return ZKB_OK;
+}
+
+// per-kernel-class device time (bench.py's roofline: average launch duration of the dominant kernel measured live, on the stream)
+extern "C" int32_t zkb_prof_enable(zkb_ctx *ctx, int32_t on) {
+    ZKB_ARG(ctx);
+    ctx->prof_on = on != 0;
+    return ZKB_OK;
+}
+extern "C" int32_t zkb_prof_read(zkb_ctx *ctx, int32_t cls, uint64_t *launches, double *ms, int32_t reset) {
+    ZKB_ARG(ctx && cls >= 0 && cls < 4);
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+    for (auto &pp : ctx->prof_pending) {
+        ZKB_CUDA(cudaEventSynchronize(pp.b));
+        float t = 0;
+        ZKB_CUDA(cudaEventElapsedTime(&t, pp.a, pp.b));
+        ctx->prof_ms[pp.cls] += t;
+        ctx->prof_count[pp.cls]++;
+        ctx->prof_free.push_back(pp.a);
+        ctx->prof_free.push_back(pp.b);
+    }
+    ctx->prof_pending.clear();
+    if (launches) *launches = ctx->prof_count[cls];
+    if (ms) *ms = ctx->prof_ms[cls];
+    if (reset) { for (int i = 0; i < 4; ++i) { ctx->prof_ms[i] = 0; ctx->prof_count[i] = 0; } }
     return ZKB_OK;
 }
 

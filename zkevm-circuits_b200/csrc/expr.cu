@@ -52,6 +52,7 @@ int32_t expr_run_device(zkb_ctx *ctx, const Instr *d_code, uint32_t ncode, int n
     ExprLaunch L{d_code, ncode, d_cols, d_consts, d_outs, log_n, out_stride, out_offset};
     const uint32_t n = 1u << log_n;
     const unsigned blocks = (n + 127) / 128;
+    ProfScope ps_(ctx, PROF_EXPR, st);
     if (nregs <= 8) expr_kernel<8><<<blocks, 128, 0, st>>>(L);
     else if (nregs <= 16) expr_kernel<16><<<blocks, 128, 0, st>>>(L);
     else if (nregs <= 32) expr_kernel<32><<<blocks, 128, 0, st>>>(L);

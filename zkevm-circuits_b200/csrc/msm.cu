@@ -527,6 +527,7 @@ int32_t msm_g1_batch_device_ex(zkb_ctx *ctx, const Fr *const *d_scalar_cols, uin
     // level 0: one thread per 32-entry chunk of the sorted list (grid from the bound; surplus threads exit on the device-side total)
     {
         const uint64_t max_chunks = (pairs + CHUNK - 1) / CHUNK;
+        ProfScope ps_(ctx, PROF_MSM_ACC, st);
         msm_acc_chunk_kernel<<<(unsigned)((max_chunks + 127) / 128), 128, 0, st>>>(bases, offsets, sorted, toff[0], nbuckets, part[0]);
     }
     ctx->launches += 4;

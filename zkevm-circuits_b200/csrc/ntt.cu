@@ -659,7 +659,10 @@ int32_t ntt_fr_batch_device_ex(zkb_ctx *ctx, const Fr *const *h_src, Fr *const *
         ZKB_ARG((uint64_t)p.tiles_per_col * count < (1ull << 32));
         const uint32_t max_ctas = (uint32_t)ctx->sm_count * NTT_CTAS_PER_SM;
         const uint32_t grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
-        ntt_tile_kernel<<<grid, NTT_THREADS, pass_smem_bytes(g), st>>>(p);
+        {
+            ProfScope ps_(ctx, PROF_NTT, st);
+            ntt_tile_kernel<<<grid, NTT_THREADS, pass_smem_bytes(g), st>>>(p);
+        }
         ctx->launches++;
     }
     ZKB_CUDA(cudaGetLastError());

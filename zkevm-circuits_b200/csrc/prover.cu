@@ -110,6 +110,14 @@ __global__ void sub_low_kernel(Fr *__restrict__ out, const Fr *__restrict__ low,
     if (i < k) fp_store(out + i, fp_sub(fp_load(out + i), fp_load(low + i)));
 }
 
+// out[j + E * i] = parts[j * n + i]  (coset parts gathered as rows -> extended-domain order)
+__global__ void interleave_parts_kernel(const Fr *__restrict__ parts, Fr *__restrict__ out, uint32_t log_n, uint32_t E) {
+    const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (idx >= ((uint64_t)E << log_n)) return;
+    const uint64_t j = idx % E, i = idx / E;
+    fp_store(out + idx, fp_load(parts + (j << log_n) + i));
+}
+
 // ---- multiplicities of the mv-lookup: open-addressing hash table keyed by the 32-byte compressed table value --------
 __device__ __forceinline__ uint32_t key_hash(const Fr &k) {
     uint32_t h = 0x9e3779b9u;
@@ -320,34 +328,47 @@ static int32_t commit_many_local(zkb_pk *pk, const std::vector<Fr *> &cols, cons
     }
     return ZKB_OK;
 }
-// commit several columns against the same bases with batched MSMs.  With a communicator, column i is committed by rank
-// i mod P and the 64-byte results are exchanged by one all-reduce (u64 sum of disjoint supports = gather).
-static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Affine *bases, uint64_t len, std::vector<G1Affine> &out, cudaStream_t st) {
-    zkb_ctx *ctx = pk->ctx;
-    if (ctx->nranks <= 1 || cols.size() < 2) return commit_many_local(pk, cols, bases, len, out, st);
-    std::vector<Fr *> mine;
-    std::vector<size_t> mine_idx;
-    for (size_t i = 0; i < cols.size(); ++i)
-        if ((int)(i % ctx->nranks) == ctx->rank) { mine.push_back(cols[i]); mine_idx.push_back(i); }
-    std::vector<G1Affine> part;
-    if (!mine.empty()) ZKB_TRY(commit_many_local(pk, mine, bases, len, part, st));
-    out.assign(cols.size(), G1Affine{Fq::zero(), Fq::zero()});
-    for (size_t t = 0; t < mine_idx.size(); ++t) out[mine_idx[t]] = part[t];
-    G1Affine *d_buf = nullptr;
-    ZKB_TRY(scratch_get(ctx, SCR_COMM, cols.size() * sizeof(G1Affine), (void **)&d_buf));
-    ZKB_CUDA(cudaMemcpyAsync(d_buf, out.data(), cols.size() * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
-    ZKB_TRY(comm_allreduce_u64(ctx, d_buf, cols.size() * 8, st));
-    ZKB_CUDA(cudaMemcpyAsync(out.data(), d_buf, cols.size() * sizeof(G1Affine), cudaMemcpyDeviceToHost, st));
-    ZKB_CUDA(cudaStreamSynchronize(st));
-    return ZKB_OK;
+// multi-GPU dealing of independent units (columns, lookup arguments, coset parts): the `count` units are cut into P contiguous
+// blocks of blk = ceil(count / P), rank r computes block r.  Results live in a slab of P * blk unit slots (the tail of the last
+// blocks is padding), so ONE in-place ncclAllGather (every rank contributes its own block, 1/P of the slab) completes it -- no
+// zero filling, no arithmetic on the wire (round 1 used an all-reduce over a zero-initialised slab: P times the bytes).
+struct Deal {
+    size_t count = 0, blk = 0;
+    int P = 1, rank = 0;
+    bool on = false;
+    Deal(const zkb_ctx *c, size_t n) : count(n), P(c->nranks), rank(c->rank) {
+        on = P > 1 && n >= 2;
+        blk = on ? (n + P - 1) / P : n;
+    }
+    bool mine(size_t i) const { return !on || (int)(i / blk) == rank; }
+    size_t padded() const { return on ? (size_t)P * blk : count; }
+};
+static int32_t deal_gather(zkb_ctx *ctx, const Deal &d, void *slab, size_t unit_bytes, cudaStream_t st) {
+    if (!d.on) return ZKB_OK;
+    return comm_allgather(ctx, (const uint8_t *)slab + (size_t)d.rank * d.blk * unit_bytes, slab, d.blk * unit_bytes, st);
 }
 
-// multi-GPU dealing of independent units: unit i of `count` is computed by rank i mod P (everything local on one GPU or when
-// there is a single unit); results are written into a zero-initialised slab and gathered by one all-reduce
-static inline bool unit_owned(const zkb_ctx *ctx, size_t i, size_t count) {
-    return ctx->nranks <= 1 || count < 2 || (int)(i % ctx->nranks) == ctx->rank;
+// commit several columns against the same bases with batched MSMs.  With a communicator the columns are dealt in contiguous blocks
+// (Deal) and the 64-byte results are all-gathered.
+static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Affine *bases, uint64_t len, std::vector<G1Affine> &out, cudaStream_t st) {
+    zkb_ctx *ctx = pk->ctx;
+    const Deal d(ctx, cols.size());
+    if (!d.on) return commit_many_local(pk, cols, bases, len, out, st);
+    std::vector<Fr *> mine;
+    for (size_t i = 0; i < cols.size(); ++i)
+        if (d.mine(i)) mine.push_back(cols[i]);
+    std::vector<G1Affine> part;
+    if (!mine.empty()) ZKB_TRY(commit_many_local(pk, mine, bases, len, part, st));
+    G1Affine *d_buf = nullptr;
+    ZKB_TRY(scratch_get(ctx, SCR_COMM, d.padded() * sizeof(G1Affine), (void **)&d_buf));
+    if (!part.empty()) ZKB_CUDA(cudaMemcpyAsync(d_buf + (size_t)d.rank * d.blk, part.data(), part.size() * sizeof(G1Affine), cudaMemcpyHostToDevice, st));
+    ZKB_TRY(deal_gather(ctx, d, d_buf, sizeof(G1Affine), st));
+    out.resize(d.padded());
+    ZKB_CUDA(cudaMemcpyAsync(out.data(), d_buf, d.padded() * sizeof(G1Affine), cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(cudaStreamSynchronize(st));
+    out.resize(cols.size());
+    return ZKB_OK;
 }
-static inline bool units_dealt(const zkb_ctx *ctx, size_t count) { return ctx->nranks > 1 && count >= 2; }
 
 // program bundle uploaded to the device
 struct DeviceProgram {
@@ -850,13 +871,13 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
         phase_idx.push_back(c);
     }
     const size_t ncols = phase_src.size();
+    const Deal deal(pk->ctx, ncols);
     Fr *slab = nullptr;
-    ZKB_TRY(s->pool.fr(ncols * n, &slab));
+    ZKB_TRY(s->pool.fr(std::max<size_t>(1, deal.padded()) * n, &slab));
     std::vector<Fr *> phase_cols(ncols);
     for (size_t i = 0; i < ncols; ++i) { phase_cols[i] = slab + i * n; s->adv_values[phase_idx[i]] = phase_cols[i]; }
-    const bool dealt = units_dealt(pk->ctx, ncols);
+    const bool dealt = deal.on;
     ZKB_CUDA(cudaStreamSynchronize(st));  // the destination block may still be in use by work queued on `st`
-    if (dealt) ZKB_CUDA(cudaMemsetAsync(slab, 0, ncols * n * sizeof(Fr), pk->ctx->copy_stream));
     const uint32_t maxb = msm_max_batch(n);
     const size_t nbatch = dealt ? 1 : (ncols + maxb - 1) / maxb;
     struct EventList {   // destroyed on every exit path
@@ -869,8 +890,8 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
         ZKB_CUDA(cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming));
         const size_t lo = dealt ? 0 : b * maxb, hi = dealt ? ncols : std::min(ncols, (b + 1) * (size_t)maxb);
         for (size_t i = lo; i < hi; ++i)
-            if (unit_owned(pk->ctx, i, ncols))
-                ZKB_CUDA(cudaMemcpyAsync(phase_cols[i], phase_src[i], n * sizeof(Fr), cudaMemcpyHostToDevice, pk->ctx->copy_stream));
+            if (deal.mine(i))
+                ZKB_CUDA(cudaMemcpyAsync(phase_cols[i], phase_src[i], n * sizeof(Fr), cudaMemcpyDefault, pk->ctx->copy_stream));   // host (pinned or pageable) or device-resident columns
         ZKB_CUDA(cudaEventRecord(evs[b], pk->ctx->copy_stream));
     }
     for (size_t b = 0; b < nbatch; ++b) {
@@ -878,10 +899,10 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
         const size_t lo = dealt ? 0 : b * maxb, hi = dealt ? ncols : std::min(ncols, (b + 1) * (size_t)maxb);
         std::vector<Fr *> part(phase_cols.begin() + lo, phase_cols.begin() + hi);
         std::vector<G1Affine> cms;
-        ZKB_TRY(commit_many(pk, part, pk->g_lagrange, n, cms, st));   // dealt: column i of the phase -> rank i mod P
+        ZKB_TRY(commit_many(pk, part, pk->g_lagrange, n, cms, st));   // dealt: the same contiguous blocks as the uploads (same unit count)
         for (auto &cm : cms) ZKB_TRY(tr_write_point(s, cm));
     }
-    if (dealt) ZKB_TRY(comm_allreduce_u64(pk->ctx, slab, ncols * n * 4, st));
+    ZKB_TRY(deal_gather(pk->ctx, deal, slab, n * sizeof(Fr), st));   // column data of the other ranks' blocks over NVLink
     for (uint32_t i = 0; i < cs.nch; ++i) {
         if (cs.ch_phase[i] == phase) {
             s->challenges[i] = tr_squeeze(s);
@@ -965,16 +986,16 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     std::vector<std::vector<Fr *>> lk_f(nl);   // compressed inputs per lookup / input set
     std::vector<Fr *> lk_t(nl), lk_m(nl);
     // multi-GPU: lookup argument l is prepared by rank l mod P; m columns live in one slab (+ one word carrying error counts)
-    const bool lk_dealt = units_dealt(ctx, nl);
+    const Deal lk_deal(ctx, nl);
+    const bool lk_dealt = lk_deal.on;
     Fr *m_slab = nullptr;
     if (nl) {
-        ZKB_TRY(pool.fr(nl * n + 1, &m_slab));
-        if (lk_dealt) ZKB_CUDA(cudaMemsetAsync(m_slab, 0, (nl * n + 1) * sizeof(Fr), st));
+        ZKB_TRY(pool.fr(lk_deal.padded() * n, &m_slab));
         for (size_t l = 0; l < nl; ++l) lk_m[l] = m_slab + l * n;
     }
     uint64_t lookup_errors = 0;
     for (size_t l = 0; l < nl; ++l) {
-        if (!unit_owned(ctx, l, nl)) continue;
+        if (!lk_deal.mine(l)) continue;
         const CsfLookup &lk = cs.lookups[l];
         ExprBuilder eb;
         ProgramBuilder pb(eb);
@@ -1022,10 +1043,13 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         }
     }
     if (lk_dealt) {
-        ZKB_CUDA(cudaMemcpyAsync(m_slab + nl * n, &lookup_errors, 8, cudaMemcpyHostToDevice, st));
-        ZKB_TRY(comm_allreduce_u64(ctx, m_slab, (nl * n + 1) * 4, st));
+        ZKB_TRY(deal_gather(ctx, lk_deal, m_slab, n * sizeof(Fr), st));
+        uint64_t *d_errw = nullptr;   // every rank learns about an unsatisfied lookup before anyone leaves the collective sequence
+        ZKB_TRY(scratch_get(ctx, SCR_COMM_FLAG, 64, (void **)&d_errw));
+        ZKB_CUDA(cudaMemcpyAsync(d_errw + 1, &lookup_errors, 8, cudaMemcpyHostToDevice, st));
+        ZKB_TRY(comm_allreduce_u64(ctx, d_errw + 1, 1, st));
         uint64_t total_err = 0;
-        ZKB_CUDA(cudaMemcpyAsync(&total_err, m_slab + nl * n, 8, cudaMemcpyDeviceToHost, st));
+        ZKB_CUDA(cudaMemcpyAsync(&total_err, d_errw + 1, 8, cudaMemcpyDeviceToHost, st));
         ZKB_CUDA(cudaStreamSynchronize(st));
         if (total_err) {
             if (!lookup_errors) set_error("a lookup input row is not in the table (reported by another rank)");
@@ -1101,12 +1125,11 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     std::vector<Fr *> phis(nl);
     Fr *phi_slab = nullptr;
     if (nl) {
-        ZKB_TRY(pool.fr(nl * n, &phi_slab));
-        if (lk_dealt) ZKB_CUDA(cudaMemsetAsync(phi_slab, 0, nl * n * sizeof(Fr), st));
+        ZKB_TRY(pool.fr(lk_deal.padded() * n, &phi_slab));
         for (size_t l = 0; l < nl; ++l) phis[l] = phi_slab + l * n;
     }
     for (size_t l = 0; l < nl; ++l) {
-        if (!unit_owned(ctx, l, nl)) continue;
+        if (!lk_deal.mine(l)) continue;
         const size_t J = lk_f[l].size();
         // denominators (f_j + beta), (t + beta) into one contiguous array, inverted at once
         Fr *dens, *invs, *dterm;
@@ -1153,7 +1176,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(prefix_sum_device(ctx, dterm, n, Fr::zero(), phis[l], st));
         ZKB_CUDA(cudaMemcpyAsync(phis[l] + (n - bf), phi_blinds + 4ull * bf * l, (size_t)bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
     }
-    if (lk_dealt) ZKB_TRY(comm_allreduce_u64(ctx, phi_slab, nl * n * 4, st));
+    if (nl) ZKB_TRY(deal_gather(ctx, lk_deal, phi_slab, n * sizeof(Fr), st));
     {
         std::vector<G1Affine> cms;
         ZKB_TRY(commit_many(pk, phis, pk->g_lagrange, n, cms, st));
@@ -1187,15 +1210,14 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         polys.resize(vals.size());
         if (vals.empty()) return ZKB_OK;
         Fr *pslab = nullptr;
-        ZKB_TRY(pool.fr(vals.size() * n, &pslab));
+        const Deal dc(ctx, vals.size());   // multi-GPU: contiguous blocks of columns per rank, completed by one all-gather
+        ZKB_TRY(pool.fr(dc.padded() * n, &pslab));
         for (size_t i = 0; i < vals.size(); ++i) polys[i] = pslab + i * n;
-        const bool dealt = units_dealt(ctx, vals.size());   // multi-GPU: column i -> rank i mod P, gathered by one all-reduce
-        if (dealt) ZKB_CUDA(cudaMemsetAsync(pslab, 0, vals.size() * n * sizeof(Fr), st));
         std::vector<Fr *> src, dst;
         for (size_t i = 0; i < vals.size(); ++i)
-            if (unit_owned(ctx, i, vals.size())) { src.push_back(vals[i]); dst.push_back(polys[i]); }
+            if (dc.mine(i)) { src.push_back(vals[i]); dst.push_back(polys[i]); }
         if (!src.empty()) ZKB_TRY(ntt_many(src, dst, pk->omega_inv, &pk->n_inv, nullptr));
-        if (dealt) ZKB_TRY(comm_allreduce_u64(ctx, pslab, vals.size() * n * 4, st));
+        ZKB_TRY(deal_gather(ctx, dc, pslab, n * sizeof(Fr), st));
         return ZKB_OK;
     };
     std::vector<Fr *> adv_polys, z_polys, phi_polys, m_polys;
@@ -1330,9 +1352,18 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     ZKB_TRY(pool.alloc(qcols.size() * sizeof(Fr *) + 8, (void **)&d_qcols));
     std::vector<Fr *> hout{h_ext};
     ZKB_TRY(upload_table(pool, hout, &d_hout, st));
-    if (ctx->nranks > 1) ZKB_CUDA(cudaMemsetAsync(h_ext, 0, pk->N * sizeof(Fr), st));
+    // multi-GPU: coset parts are dealt in contiguous blocks; a rank writes its parts as contiguous n-element rows of h_parts, the rows
+    // are all-gathered and interleaved into the extended-domain order h_ext[j + E i] the inverse transform expects
+    const Deal dq(ctx, pk->E);
+    Fr *h_parts = nullptr;
+    if (dq.on) {
+        ZKB_TRY(pool.fr(dq.padded() * n, &h_parts));
+        std::vector<Fr *> hp{h_parts};
+        ZKB_CUDA(cudaMemcpyAsync(d_hout, hp.data(), sizeof(Fr *), cudaMemcpyHostToDevice, st));
+        ZKB_CUDA(cudaStreamSynchronize(st));
+    }
     for (uint32_t j = 0; j < pk->E; ++j) {
-        if (ctx->nranks > 1 && (int)(j % ctx->nranks) != ctx->rank) continue;  // coset part j belongs to rank j mod P
+        if (!dq.mine(j)) continue;
         const Fr gj = fp_mul(pk->zeta, fp_pow_u64(pk->ext_omega, j));
         ZKB_TRY(fr_powers_device(ctx, gj, n, pows, st));
         ZKB_TRY(ntt_many(ntt_src, ntt_dst, pk->omega, nullptr, pows));
@@ -1343,10 +1374,15 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         Instr tail{OP_STOREACC, 0, 0, 0, 0u | (tinv_idx[j] << 8)};
         ZKB_CUDA(cudaMemcpyAsync(d_qcols, cols_j.data(), cols_j.size() * sizeof(Fr *), cudaMemcpyHostToDevice, st));
         ZKB_CUDA(cudaMemcpyAsync(qdp.code + base_len, &tail, sizeof(Instr), cudaMemcpyHostToDevice, st));
-        ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, pk->E, j, st));
+        if (dq.on) ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, 1, (uint32_t)((uint64_t)j * n), st));
+        else ZKB_TRY(expr_run_device(ctx, qdp.code, qdp.ncode, qdp.nregs, d_qcols, qdp.consts, d_hout, k, pk->E, j, st));
         ZKB_CUDA(cudaStreamSynchronize(st));  // `tail` and `cols_j` live on the stack
     }
-    ZKB_TRY(comm_allreduce_u64(ctx, h_ext, pk->N * 4, st));  // gather the coset parts of the other ranks (no-op on one GPU)
+    if (dq.on) {
+        ZKB_TRY(deal_gather(ctx, dq, h_parts, n * sizeof(Fr), st));
+        interleave_parts_kernel<<<(unsigned)((pk->N + 255) / 256), 256, 0, st>>>(h_parts, h_ext, k, pk->E);
+        ctx->launches++;
+    }
     trace.mark("quotient: coset NTTs + fused eval");
     // extended_to_coeff: inverse NTT over the extended domain, 1/N, undo the zeta coset, keep n*(d-1) coefficients
     ZKB_TRY(ntt_fr_device(ctx, h_ext, h_ext, pk->ext_k, pk->ext_omega_inv, &pk->N_inv, 2, nullptr, st));

@@ -26,6 +26,8 @@ SIGNATURES = {
     "zkb_version": (ctypes.c_uint32, []),
     "zkb_launch_count": (ctypes.c_uint64, [_vp]),
     "zkb_sync": (ctypes.c_int32, [_vp]),
+    "zkb_prof_enable": (ctypes.c_int32, [_vp, ctypes.c_int32]),
+    "zkb_prof_read": (ctypes.c_int32, [_vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double), ctypes.c_int32]),
     "zkb_stream": (_vp, [_vp]),
     "zkb_malloc": (ctypes.c_int32, [_vp, ctypes.c_uint64, ctypes.POINTER(_vp)]),
     "zkb_free": (ctypes.c_int32, [_vp, _vp]),
@@ -146,6 +148,15 @@ class Context:
         buf2 = (ctypes.c_uint8 * 128).from_buffer_copy(raw)
         check(self.lib.zkb_comm_init(self.handle, ctypes.cast(buf2, _vp), rank, world))
         return rank, world
+
+    def prof_enable(self, on=True):
+        check(self.lib.zkb_prof_enable(self.handle, 1 if on else 0))
+
+    def prof_read(self, cls, reset=False):
+        """-> (launches, total ms) of kernel class cls (0 ntt_tile, 1 msm_acc_chunk, 2 expr) since the last reset."""
+        n, ms = ctypes.c_uint64(0), ctypes.c_double(0)
+        check(self.lib.zkb_prof_read(self.handle, int(cls), ctypes.byref(n), ctypes.byref(ms), 1 if reset else 0))
+        return int(n.value), float(ms.value)
 
     @property
     def launch_count(self):

@@ -108,10 +108,27 @@ def validate_csf(blob):
 
 
 def _ptr_array(arrs):
-    """host numpy arrays (or None) -> (keepalive list, void** as c_void_p array)."""
-    keep = [np.ascontiguousarray(a) if a is not None else None for a in arrs]
-    tbl = (ctypes.c_void_p * max(1, len(keep)))(*[a.ctypes.data if a is not None else None for a in keep])
+    """host numpy arrays, device buffers (objects with a `device_ptr` attribute) or None -> (keepalive list, void** as c_void_p array)."""
+    keep, ptrs = [], []
+    for a in arrs:
+        if a is None:
+            keep.append(None); ptrs.append(None)
+        elif hasattr(a, "device_ptr"):
+            keep.append(a); ptrs.append(int(a.device_ptr))
+        else:
+            c = np.ascontiguousarray(a)
+            keep.append(c); ptrs.append(c.ctypes.data)
+    tbl = (ctypes.c_void_p * max(1, len(keep)))(*ptrs)
     return keep, tbl
+
+
+class DeviceColumn:
+    """a witness column that already lives in HBM (torch tensor or raw pointer): zkb_prove_advice_phase copies it device-to-device"""
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.device_ptr = tensor.data_ptr()
+        self.shape = tuple(tensor.shape)
+        self.dtype = np.dtype(np.uint64)
 
 
 class ProvingKey:
