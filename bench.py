@@ -223,6 +223,9 @@ def proof_accounting(shape, launches_by_class):
 
 
 def verify_with_oracle(sc, pk, proof, inst_host, fixed_host, sigma_host):
+    """the checker leg: oracle verifier on a proof the GPU produced (outside every timed region)"""
+    if os.path.join(ROOT, "oracle") not in sys.path:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from test_gpu_standins import verify_gpu_proof
     ok, rejected, checked = verify_gpu_proof(sc, pk, proof, inst_host, SRS_S, fixed_host, sigma_host)
     return {"verified": bool(ok), "tampered_rejected": bool(rejected), "vk_commitments_checked_by_trapdoor": checked,

@@ -248,6 +248,23 @@ ZKB_API int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4], c
  * points absorbed AND written uncompressed as x || y big-endian (64 B), scalars 32 B big-endian, challenge = keccak256(buffer) mod r.   */
 ZKB_API int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const uint64_t transcript_repr[4],
                                    const uint64_t *const *instance_values, const uint32_t *instance_lens, zkb_session **out);
+/* 3 = THE CALLER'S transcript: create_proof is generic over `T: TranscriptWrite<G1Affine, Challenge255<G1Affine>>` (and the SDK
+ * instantiates it with Blake2b, Poseidon and Keccak transcripts), and a generic type cannot cross a C ABI -- but its four
+ * operations can.  The shim passes a table of extern "C" trampolines around the `&mut T` it was handed; the session then calls
+ * exactly the sequence halo2's prover would (common_scalar for vk.transcript_repr and the instances, write_point per commitment,
+ * squeeze_challenge, write_scalar per evaluation), so ANY transcript -- including ones this library has never seen -- produces its
+ * own proof bytes on the Rust side and the RNG-free session needs no replay.  Scalars are Fr in halo2curves' Montgomery layout,
+ * points G1Affine x || y; a callback returns 0 or an error code that aborts the session (ZKB_ERR_STATE).  In this mode
+ * zkb_prove_finish reports proof_len = 0: the bytes live in the caller's writer.                                                */
+typedef struct zkb_transcript_vtable {
+    void *user;
+    int32_t (*common_scalar)(void *user, const uint64_t scalar[4]);
+    int32_t (*write_scalar)(void *user, const uint64_t scalar[4]);
+    int32_t (*write_point)(void *user, const uint64_t point_xy[8]);
+    int32_t (*squeeze_challenge)(void *user, uint64_t challenge_out[4]);
+} zkb_transcript_vtable;
+ZKB_API int32_t zkb_prove_begin_cb(zkb_pk *pk, const zkb_transcript_vtable *vt, const uint64_t transcript_repr[4],
+                                   const uint64_t *const *instance_values, const uint32_t *instance_lens, zkb_session **out);
 /* Host-only transcript primitives (no CUDA device needed; used by the CPU test-suite to pin the session's hashers):
  * zkb_poseidon_hash_host        absorb n Fr (Montgomery) into a fresh PoseidonTranscript sponge, squeeze one challenge
  * zkb_blake2b_challenge_host    feed bytes to a fresh Blake2b("Halo2-Transcript") state, squeeze one Challenge255 (mod r)

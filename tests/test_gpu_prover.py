@@ -196,3 +196,39 @@ def test_prove_finish_query_then_fetch():
     blinds = {"z": tc.blinds_ints["z"], "phi": tc.blinds_ints["phi"], "random_poly": F.arr(tc.blinds_ints["random_poly"])}
     proof_ref, _ = ref.create_proof(pkr, tc.transcript_repr, tc.instances, lambda ph, ch: {c: F.arr(v) for c, v in tc.advice_ints(ph, ch).items()}, blinds)
     assert bytes(out) == proof_ref
+
+
+def test_callers_transcript_through_callbacks_writes_the_same_proof():
+    """create_proof's generic `T: TranscriptWrite`: the session drives a transcript object that lives on the CALLER's side
+    through zkb_transcript_vtable.  Here that object is the oracle's Blake2b transcript (hashlib): the bytes it writes must equal the
+    proof of the in-library Blake2b session, and an exception raised inside a callback must surface as an error, not a crash."""
+    from zkb200 import plonk as Z
+    from zkb200.lib import ZkbError
+    tc = ToyCircuit(7, seed=321)
+    ref = H.Ref(tc.cs, 1234)
+    F = ref.F
+    fixed = [F.arr(c) for c in tc.fixed_ints]
+    pkr = ref.keygen(fixed, tc.copies)
+    rp = F.arr(tc.blinds_ints["random_poly"])
+    pk = Z.ProvingKey(to_product_cs(tc.cs, ref.bf, ref.d), fixed, pkr["sigma_values"], ref.g, ref.g_lagrange)
+    synth = lambda ph, ch: {c: F.arr(v) for c, v in tc.advice_ints(ph, {i: F.ints(v[None])[0] for i, v in ch.items()}).items()}
+    args = (pk, F.arr([tc.transcript_repr])[0], [F.arr(c) for c in tc.instances], synth,
+            np.concatenate([F.arr(b) for b in tc.blinds_ints["z"]]), np.concatenate([F.arr(b) for b in tc.blinds_ints["phi"]]), rp)
+    proof_lib = Z.create_proof(*args)
+
+    class Mine:
+        def __init__(self): self.t = H.Ref.Transcript(ref); self.ops = 0
+        def common_scalar(self, l): self.ops += 1; self.t.common_scalar(F.ints(l[None])[0])
+        def write_scalar(self, l): self.ops += 1; self.t.write_scalar(F.ints(l[None])[0])
+        def write_point(self, l): self.ops += 1; self.t.write_point(l)
+        def squeeze_challenge(self): self.ops += 1; return F.arr([self.t.squeeze()])[0]
+    mine = Mine()
+    out = Z.create_proof(*args, transcript=Z.CallbackTranscript(mine))
+    assert out == b"" and bytes(mine.t.buf) == proof_lib and mine.ops > 20
+
+    class Broken(Mine):
+        def write_point(self, l): raise RuntimeError("writer full")
+    cbt = Z.CallbackTranscript(Broken())
+    with pytest.raises(ZkbError):
+        Z.create_proof(*args, transcript=cbt)
+    assert isinstance(cbt.error, RuntimeError)

@@ -102,7 +102,8 @@ def verify_gpu_proof(sc, pk, proof, inst, s, fixed, sigma, spot=((0, "fixed"), (
     vk = pk.vk_bytes()
     assert int.from_bytes(vk[:4], "big") == sc.k and int.from_bytes(vk[4:8], "big") == sc.cs.num_fixed
     pts = [P.g1_decompress(vk[8 + 32 * i: 40 + 32 * i]) for i in range((len(vk) - 8) // 32)]
-    to_aff = lambda pt: np.array(P.limbs(P.to_mont(pt[0], P.Q_MOD)) + P.limbs(P.to_mont(pt[1], P.Q_MOD)), dtype=np.uint64)
+    # an all-zero fixed column (an unused selector) commits to the identity: (0, 0) in halo2curves' affine layout
+    to_aff = lambda pt: np.zeros(8, dtype=np.uint64) if pt is None else np.array(P.limbs(P.to_mont(pt[0], P.Q_MOD)) + P.limbs(P.to_mont(pt[1], P.Q_MOD)), dtype=np.uint64)
     nf = sc.cs.num_fixed
     pkr = {"fixed_commitments": [to_aff(p) for p in pts[:nf]], "sigma_commitments": [to_aff(p) for p in pts[nf:]]}
     checked = 0

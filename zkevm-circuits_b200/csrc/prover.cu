@@ -204,8 +204,11 @@ struct zkb_pk {
 struct zkb_session {
     zkb_pk *pk = nullptr;
     // 0: Blake2bWrite<_, G1Affine, Challenge255<_>> (benches), 1: snark-verifier-sdk PoseidonTranscript (gen_snark_shplonk),
-    // 2: snark-verifier EvmTranscript over Keccak-256 (gen_evm_proof_shplonk)
+    // 2: snark-verifier EvmTranscript over Keccak-256 (gen_evm_proof_shplonk), 3: the CALLER's transcript through zkb_transcript_vtable
+    // (create_proof's generic `T: TranscriptWrite`: the shim forwards the four operations to the Rust object it was handed)
     int tkind = 0;
+    zkb_transcript_vtable vt{};
+    int32_t cb_error = 0;   // first non-zero return of a caller callback (checked after every stage)
     Blake2b tr{"Halo2-Transcript"};
     PoseidonSponge pos;
     std::vector<uint8_t> evm_buf;
@@ -243,6 +246,7 @@ static void push_be32(std::vector<uint8_t> &dst, const F &canonical) {
     for (int i = 31; i >= 0; --i) dst.push_back(b[i]);
 }
 static void tr_common_scalar(zkb_session *s, const Fr &v) {
+    if (s->tkind == 3) { const int32_t r = s->vt.common_scalar(s->vt.user, (const uint64_t *)v.l); if (r && !s->cb_error) s->cb_error = r; return; }
     if (s->tkind == 1) { s->pos.update(v); return; }
     if (s->tkind == 2) { push_be32(s->evm_buf, fp_to_canonical(v)); return; }
     const uint8_t pre = 2;
@@ -251,6 +255,7 @@ static void tr_common_scalar(zkb_session *s, const Fr &v) {
     s->tr.update(c.l, 32);
 }
 static void tr_write_scalar(zkb_session *s, const Fr &v) {
+    if (s->tkind == 3) { const int32_t r = s->vt.write_scalar(s->vt.user, (const uint64_t *)v.l); if (r && !s->cb_error) s->cb_error = r; return; }
     tr_common_scalar(s, v);
     Fr c = fp_to_canonical(v);
     if (s->tkind == 2) { push_be32(s->proof, c); return; }
@@ -259,6 +264,11 @@ static void tr_write_scalar(zkb_session *s, const Fr &v) {
 }
 static int32_t tr_write_point(zkb_session *s, const G1Affine &p) {
     if (p.is_identity()) { set_error("cannot write points at infinity to the transcript"); return ZKB_ERR_STATE; }
+    if (s->tkind == 3) {
+        const int32_t r = s->vt.write_point(s->vt.user, (const uint64_t *)&p);
+        if (r) { set_error("the caller's transcript refused a point (callback returned %d)", r); if (!s->cb_error) s->cb_error = r; return ZKB_ERR_STATE; }
+        return ZKB_OK;
+    }
     Fq x = fp_to_canonical(p.x), y = fp_to_canonical(p.y);
     if (s->tkind == 2) {  // absorbed and written uncompressed: x || y, big-endian
         push_be32(s->evm_buf, x); push_be32(s->evm_buf, y);
@@ -280,6 +290,12 @@ static int32_t tr_write_point(zkb_session *s, const G1Affine &p) {
     return ZKB_OK;
 }
 static Fr tr_squeeze(zkb_session *s) {
+    if (s->tkind == 3) {
+        Fr c = Fr::zero();
+        const int32_t r = s->vt.squeeze_challenge(s->vt.user, (uint64_t *)c.l);
+        if (r && !s->cb_error) s->cb_error = r;
+        return c;
+    }
     if (s->tkind == 1) return s->pos.squeeze();
     if (s->tkind == 2) {
         // hash the buffer (plus a 0x01 byte when it holds just the previous digest), keep the digest as the new buffer,
@@ -814,14 +830,26 @@ extern "C" int32_t zkb_prove_begin(zkb_pk *pk, const uint64_t transcript_repr[4]
                                    zkb_session **out) {
     return zkb_prove_begin_ex(pk, 0, transcript_repr, instance_values, instance_lens, out);
 }
+static int32_t prove_begin_common(zkb_pk *pk, int32_t transcript_kind, const zkb_transcript_vtable *vt, const uint64_t transcript_repr[4],
+                                  const uint64_t *const *instance_values, const uint32_t *instance_lens, zkb_session **out);
 extern "C" int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const uint64_t transcript_repr[4], const uint64_t *const *instance_values,
                                       const uint32_t *instance_lens, zkb_session **out) {
-    ZKB_ARG(pk && transcript_repr && out && (pk->cs.ni == 0 || (instance_values && instance_lens)));
     ZKB_ARG(transcript_kind >= 0 && transcript_kind <= 2);
+    return prove_begin_common(pk, transcript_kind, nullptr, transcript_repr, instance_values, instance_lens, out);
+}
+extern "C" int32_t zkb_prove_begin_cb(zkb_pk *pk, const zkb_transcript_vtable *vt, const uint64_t transcript_repr[4],
+                                      const uint64_t *const *instance_values, const uint32_t *instance_lens, zkb_session **out) {
+    ZKB_ARG(vt && vt->common_scalar && vt->write_scalar && vt->write_point && vt->squeeze_challenge);
+    return prove_begin_common(pk, 3, vt, transcript_repr, instance_values, instance_lens, out);
+}
+static int32_t prove_begin_common(zkb_pk *pk, int32_t transcript_kind, const zkb_transcript_vtable *vt, const uint64_t transcript_repr[4],
+                                  const uint64_t *const *instance_values, const uint32_t *instance_lens, zkb_session **out) {
+    ZKB_ARG(pk && transcript_repr && out && (pk->cs.ni == 0 || (instance_values && instance_lens)));
     ZKB_CUDA(cudaSetDevice(pk->ctx->device));
     std::unique_ptr<zkb_session> s(new zkb_session());
     s->pk = pk;
     s->tkind = transcript_kind;
+    if (vt) s->vt = *vt;
     s->pool.ctx = pk->ctx;
     const Csf &cs = pk->cs;
     const uint64_t n = pk->n;
@@ -847,6 +875,7 @@ extern "C" int32_t zkb_prove_begin_ex(zkb_pk *pk, int32_t transcript_kind, const
     s->adv_values.assign(cs.na, nullptr);
     s->challenges.assign(cs.nch, Fr::zero());
     ZKB_CUDA(cudaStreamSynchronize(st));
+    if (s->cb_error) { set_error("the caller's transcript callback failed (%d)", s->cb_error); return ZKB_ERR_STATE; }
     *out = s.release();
     return ZKB_OK;
 }
@@ -910,6 +939,7 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
         }
     }
     s->next_phase++;
+    if (s->cb_error) { set_error("the caller's transcript callback failed (%d)", s->cb_error); return ZKB_ERR_STATE; }
     return ZKB_OK;
 }
 
@@ -1637,6 +1667,7 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         ZKB_TRY(tr_write_point(s, cm));
     }
     trace.mark("shplonk");
+    if (s->cb_error) { set_error("the caller's transcript callback failed (%d)", s->cb_error); return ZKB_ERR_STATE; }
     s->finished = true;
     return ZKB_OK;
 }

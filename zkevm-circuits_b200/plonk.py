@@ -187,11 +187,50 @@ class ProvingKey:
 
 TRANSCRIPTS = {"blake2b": 0, "poseidon": 1, "evm": 2}
 
+_CB_SCALAR = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64))
+
+
+class _TranscriptVtable(ctypes.Structure):
+    _fields_ = [("user", ctypes.c_void_p), ("common_scalar", _CB_SCALAR), ("write_scalar", _CB_SCALAR), ("write_point", _CB_SCALAR),
+                ("squeeze_challenge", _CB_SCALAR)]
+
+
+class CallbackTranscript:
+    """zkb_transcript_vtable around a caller-side transcript object (the stand-in for create_proof's generic `T: TranscriptWrite`, which
+    the Rust shim forwards the same way).  `obj` implements common_scalar(limbs), write_scalar(limbs), write_point(limbs8) and
+    squeeze_challenge() -> 4 Montgomery limbs; limbs are numpy uint64 arrays in halo2curves' in-memory layout."""
+
+    def __init__(self, obj):
+        self.obj = obj
+        self.error = None
+
+        def wrap(fn, n_in):
+            def cb(_user, ptr):
+                try:
+                    fn(np.ctypeslib.as_array(ptr, shape=(n_in,)).copy())
+                    return 0
+                except Exception as e:   # never let a Python exception unwind through C
+                    self.error = e
+                    return 1
+            return _CB_SCALAR(cb)
+
+        def squeeze(_user, ptr):
+            try:
+                out = np.ascontiguousarray(obj.squeeze_challenge(), dtype=np.uint64)
+                for i in range(4): ptr[i] = int(out[i])
+                return 0
+            except Exception as e:
+                self.error = e
+                return 1
+        self._keep = (wrap(obj.common_scalar, 4), wrap(obj.write_scalar, 4), wrap(obj.write_point, 8), _CB_SCALAR(squeeze))
+        self.vt = _TranscriptVtable(None, *self._keep)
+
 
 def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blinds, random_poly, transcript="blake2b"):
     """Mirror of plonk::create_proof for one circuit; transcript = "blake2b" (Blake2bWrite, the reference's benches) or "poseidon"
     (snark-verifier-sdk's PoseidonTranscript, what gen_snark_shplonk uses) or "evm" (snark-verifier's EvmTranscript over Keccak-256,
-    what gen_evm_proof_shplonk uses; proof items uncompressed big-endian).
+    what gen_evm_proof_shplonk uses; proof items uncompressed big-endian) or a CallbackTranscript around the caller's own transcript
+    object (create_proof's generic `T`): then the returned bytes are empty and the proof is whatever that object wrote.
 
     transcript_repr: uint64[4] (Montgomery Fr).   instances: list of uint64 (len, 4) arrays (one per instance column).
     synthesize(phase, challenges) -> dict {advice column: uint64 (n,4) array, already blinded} for that phase's columns,
@@ -203,7 +242,11 @@ def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blind
     ki, itbl = _ptr_array(instances)
     lens = (ctypes.c_uint32 * max(1, len(instances)))(*[a.shape[0] for a in instances])
     sess = _vp()
-    check(lib.zkb_prove_begin_ex(pk.handle, TRANSCRIPTS[transcript], _vp(tr.ctypes.data), ctypes.cast(itbl, _vp), ctypes.cast(lens, _vp), ctypes.byref(sess)))
+    if isinstance(transcript, CallbackTranscript):   # the caller's own transcript object: proof bytes are written on its side
+        check(lib.zkb_prove_begin_cb(pk.handle, ctypes.cast(ctypes.pointer(transcript.vt), _vp), _vp(tr.ctypes.data), ctypes.cast(itbl, _vp),
+                                     ctypes.cast(lens, _vp), ctypes.byref(sess)))
+    else:
+        check(lib.zkb_prove_begin_ex(pk.handle, TRANSCRIPTS[transcript], _vp(tr.ctypes.data), ctypes.cast(itbl, _vp), ctypes.cast(lens, _vp), ctypes.byref(sess)))
     try:
         nch = len(cs.challenge_phase)
         ch_buf = np.zeros((max(1, nch), 4), dtype=np.uint64)
