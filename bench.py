@@ -114,7 +114,9 @@ def load_oracle():
     os.environ.setdefault("OMP_PLACES", "cores")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_lib
-    return oracle_lib.load()
+    orc = oracle_lib.load()
+    orc.set_num_threads(host_threads())     # the OpenMP runtime may already have been initialised with the launcher's value
+    return orc
 
 
 def oracle_proof_seconds(k, advice, reps=1):
@@ -222,12 +224,12 @@ def proof_accounting(shape, launches_by_class):
                                                               "value-domain programs not counted)"}}
 
 
-def verify_with_oracle(sc, pk, proof, inst_host, fixed_host, sigma_host):
-    """the checker leg: oracle verifier on a proof the GPU produced (outside every timed region)"""
-    if os.path.join(ROOT, "oracle") not in sys.path:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+def verify_with_oracle(sc, vk_bytes, proof, inst_host, fixed_host, sigma_host):
+    """the checker leg: oracle verifier on a proof the GPU produced (outside every timed region).  vk_bytes = pk.vk_bytes(), fetched
+    by the caller on EVERY rank (with a communicator that call is a collective)"""
+    load_oracle()
     from test_gpu_standins import verify_gpu_proof
-    ok, rejected, checked = verify_gpu_proof(sc, pk, proof, inst_host, SRS_S, fixed_host, sigma_host)
+    ok, rejected, checked = verify_gpu_proof(sc, vk_bytes, proof, inst_host, SRS_S, fixed_host, sigma_host)
     return {"verified": bool(ok), "tampered_rejected": bool(rejected), "vk_commitments_checked_by_trapdoor": checked,
             "verifier": "oracle/halo2_ref.py verify_proof (pinned by the reference's own k=25 proof, tests/test_fixture_proof.py)"}
 
@@ -388,7 +390,8 @@ def main():
                 "note": "dominant kernel of the proof by measured device time; all three hot kernels are bound by the integer-multiply pipe "
                         "(254-bit Montgomery arithmetic), not by HBM: see DESIGN.md section 2 and profiles/r02_microbench_pipes.txt",
                 "kernels": kernels}
-    verdict = verify_with_oracle(sc, pk, proof, inst_h, fixed_h, sigma_h) if rank == 0 else None
+    vk_bytes = pk.vk_bytes()      # collective when world > 1: every rank calls it
+    verdict = verify_with_oracle(sc, vk_bytes, proof, inst_h, fixed_h, sigma_h) if rank == 0 else None
     if rank == 0 and not (verdict["verified"] and verdict["tampered_rejected"]):
         failures.append("k=20 proof rejected by the oracle verifier")
     if world > 1:
@@ -426,7 +429,7 @@ def main():
             ph, pd, ik = make_provers(sck, pkk, pin)
             sd, _ = time_steps(pd, 2, 3, barrier)
             se, prf = time_steps(ph, 1, 3, barrier)
-            v = verify_with_oracle(sck, pkk, prf, ik, fk, sk)
+            v = verify_with_oracle(sck, pkk.vk_bytes(), prf, ik, fk, sk)
             if not (v["verified"] and v["tampered_rejected"]):
                 failures.append("k=17 proof rejected by the oracle verifier")
             extras["proof_keccak_shape_k17"] = {"shape": {**sck.shape, **setk}, "proof_bytes": len(prf), "seconds_device_resident_witness": sd,

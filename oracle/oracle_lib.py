@@ -30,6 +30,11 @@ class Oracle:
     def num_threads(self):
         return self.lib.zko_num_threads()
 
+    def set_num_threads(self, n):
+        """omp_set_num_threads: overrides an OMP_NUM_THREADS=1 inherited from a launcher (torchrun does that to its workers)"""
+        self.lib.zko_set_num_threads(ctypes.c_int(int(n)))
+        return self.num_threads()
+
     def field_binop(self, which, op, a, b):
         out = np.empty_like(a)
         self.lib.zko_field_binop(which, op, _p(a), _p(b), _p(out), ctypes.c_uint64(a.shape[0]))

@@ -27,6 +27,11 @@
 #define FR (&ZKO_FR)
 #define API __attribute__((visibility("default")))
 
+/* explicit thread count: launchers (torchrun) export OMP_NUM_THREADS=1 to their workers, which would silently turn the CPU baseline
+ * into a single-thread run; the harness sets the count it wants and reports what it got */
+API void zko_set_num_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+}
 API int zko_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

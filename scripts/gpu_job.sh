@@ -7,6 +7,6 @@ if [ -z "$NO_BENCH" ]; then timeout 900 python bench.py ${BENCH_FLAGS:---steps 5
 if [ -x scripts/microbench/pipes ] && [ -n "$PIPES" ]; then timeout 60 ./scripts/microbench/pipes > gpurun_out/${T}_pipes.txt 2>&1; fi
 if [ -n "$NCU_NTT" ]; then timeout 300 ncu --set full --clock-control none --import-source on -k regex:ntt_tile_kernel -s 3 -c 3 -o gpurun_out/${T}_ntt -f python scripts/prof_kernels.py ntt > gpurun_out/${T}_ncu_ntt.log 2>&1; fi
 if [ -n "$NCU_MSM" ]; then timeout 300 ncu --set full --clock-control none --import-source on -k regex:"msm_acc_chunk|msm_wsum_level|msm_acc_levelN|msm_digits" -s 8 -c 8 -o gpurun_out/${T}_msm -f python scripts/prof_kernels.py msm > gpurun_out/${T}_ncu_msm.log 2>&1; fi
-if [ -n "$MULTI" ]; then timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $MULTI --master-addr 127.0.0.1 --master-port 29517 scripts/multi_gpu_check.py ${MULTI_ARGS} > gpurun_out/${T}_multi.log 2>&1; echo "multi rc=$?"; tail -3 gpurun_out/${T}_multi.log | cut -c1-2500; fi
-if [ -n "$MULTI_BENCH" ]; then ZKB_TRACE=${ZKB_TRACE} timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $MULTI_BENCH --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $MULTI_BENCH --steps 3 --warmup 3 > gpurun_out/${T}_mbench.log 2> gpurun_out/${T}_mbench.err; echo "mbench rc=$?"; tail -1 gpurun_out/${T}_mbench.log | cut -c1-3000; grep -v "^W0\|^\*\*\*\|^$" gpurun_out/${T}_mbench.err | tail -40; fi
+if [ -n "$MULTI" ]; then timeout ${MULTI_TIMEOUT:-300} python -m torch.distributed.run --nnodes=1 --nproc-per-node $MULTI --master-addr 127.0.0.1 --master-port 29517 scripts/multi_gpu_check.py ${MULTI_ARGS} > gpurun_out/${T}_multi.log 2>&1; echo "multi rc=$?"; tail -3 gpurun_out/${T}_multi.log | cut -c1-2500; fi
+if [ -n "$MULTI_BENCH" ]; then ZKB_TRACE=${ZKB_TRACE} timeout ${MBENCH_TIMEOUT:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $MULTI_BENCH --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $MULTI_BENCH --steps 3 --warmup 3 > gpurun_out/${T}_mbench.log 2> gpurun_out/${T}_mbench.err; echo "mbench rc=$?"; tail -1 gpurun_out/${T}_mbench.log | cut -c1-3000; grep -v "^W0\|^\*\*\*\|^$" gpurun_out/${T}_mbench.err | tail -40; fi
 ls -la gpurun_out | tail -8

@@ -94,12 +94,13 @@ def trapdoor_commit_lagrange(F, values_mont, k, s):
     return P.g1_mul(P.G1_GEN, fs)
 
 
-def verify_gpu_proof(sc, pk, proof, inst, s, fixed, sigma, spot=((0, "fixed"), (-1, "sigma"))):
-    """oracle verifier over the device's vk; -> (accepted, number of vk commitments cross-checked by the trapdoor)"""
+def verify_gpu_proof(sc, pk_or_vk, proof, inst, s, fixed, sigma, spot=((0, "fixed"), (-1, "sigma"))):
+    """oracle verifier over the device's vk (a ProvingKey, or its vk_bytes()); -> (accepted, tampered proof rejected, number of vk
+    commitments cross-checked by the trapdoor)"""
     cs = to_oracle_cs(sc.cs)
     ref = H.Ref(cs, s, build_srs=False)
     F = ref.F
-    vk = pk.vk_bytes()
+    vk = pk_or_vk if isinstance(pk_or_vk, (bytes, bytearray)) else pk_or_vk.vk_bytes()
     assert int.from_bytes(vk[:4], "big") == sc.k and int.from_bytes(vk[4:8], "big") == sc.cs.num_fixed
     pts = [P.g1_decompress(vk[8 + 32 * i: 40 + 32 * i]) for i in range((len(vk) - 8) // 32)]
     # an all-zero fixed column (an unused selector) commits to the identity: (0, 0) in halo2curves' affine layout

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128) expr_kernel(ExprLaunch L) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     Fr regs[NREGS];
-    Fr acc = Fr::zero();
+    Fr acc = Fr::zero(), acc2 = Fr::zero();
     for (uint32_t pc = 0; pc < L.ncode; ++pc) {
         const Instr in = L.code[pc];
         switch (in.op) {
@@ -41,6 +41,11 @@ __global__ void __launch_bounds__(128) expr_kernel(ExprLaunch L) {
             fp_store(L.outs[in.imm & 0xffu] + (size_t)row * L.out_stride + L.out_offset, fp_mul(acc, fp_load(L.consts + (in.imm >> 8))));
             break;
         case OP_CLEARACC: acc = Fr::zero(); break;
+        case OP_HORNER2: acc2 = fp_add(fp_mul(acc2, fp_load(L.consts + in.imm)), regs[in.a]); break;
+        case OP_FOLD:
+            acc = fp_add(fp_mul(acc, fp_load(L.consts + in.imm)), fp_mul(regs[in.a], acc2));
+            acc2 = Fr::zero();
+            break;
         default: break;
         }
     }

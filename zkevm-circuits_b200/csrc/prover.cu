@@ -1285,8 +1285,41 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     const uint32_t y_idx = qeb.const_slot(y);
     {
         std::vector<int64_t> memo(cs.nodes.size(), -1);
-        for (uint32_t gnode : cs.gates) {
-            if (!qpb.scope({{translate(cs, gnode, qeb, qsm, s->challenges, memo), ProgramBuilder::HORNER, y_idx}})) { set_error("gate: %s", qpb.error.c_str()); return ZKB_ERR_ARG; }
+        // Gate polynomials, Horner in y in constraint-system order.  Circuits multiply whole groups of constraints by one selector
+        // (`q_enable * constraint`), so runs of CONSECUTIVE gates of the form fixed(col, rot) * t_j are folded exactly:
+        //   (..(acc y + f t_1) y + ..) y + f t_r  =  acc y^r + f (t_1 y^(r-1) + .. + t_r)
+        // -- the same field element (distributivity is exact mod r), one multiply per gate less than the term-by-term form.
+        auto selector_split = [&](uint32_t gnode, uint32_t &sel, uint32_t &rest) -> bool {
+            const auto &nd = cs.nodes[gnode];
+            if (nd[0] != N_MUL) return false;
+            for (int side = 0; side < 2; ++side) {
+                const uint32_t a = nd[1 + side], b = nd[2 - side];
+                if (cs.nodes[a][0] == N_FIXED) { sel = a; rest = b; return true; }
+            }
+            return false;
+        };
+        auto same_query = [&](uint32_t a, uint32_t b) { return cs.nodes[a][1] == cs.nodes[b][1] && cs.nodes[a][2] == cs.nodes[b][2]; };
+        const bool fold_runs = !(getenv("ZKB_NO_SELECTOR_FOLD") && getenv("ZKB_NO_SELECTOR_FOLD")[0] == '1');
+        for (size_t gi = 0; gi < cs.gates.size();) {
+            uint32_t sel = 0, rest = 0;
+            size_t run = 1;
+            if (fold_runs && selector_split(cs.gates[gi], sel, rest)) {
+                uint32_t s2 = 0, r2 = 0;
+                while (gi + run < cs.gates.size() && run < 4096 && selector_split(cs.gates[gi + run], s2, r2) && same_query(sel, s2)) ++run;
+            }
+            if (run < 2) {
+                if (!qpb.scope({{translate(cs, cs.gates[gi], qeb, qsm, s->challenges, memo), ProgramBuilder::HORNER, y_idx}})) { set_error("gate: %s", qpb.error.c_str()); return ZKB_ERR_ARG; }
+                ++gi;
+                continue;
+            }
+            for (size_t t = 0; t < run; ++t) {
+                uint32_t s2 = 0, r2 = 0;
+                selector_split(cs.gates[gi + t], s2, r2);
+                if (!qpb.scope({{translate(cs, r2, qeb, qsm, s->challenges, memo), ProgramBuilder::HORNER2, y_idx}})) { set_error("gate: %s", qpb.error.c_str()); return ZKB_ERR_ARG; }
+            }
+            const uint32_t yr_idx = qeb.const_slot(fp_pow_u64(y, run));
+            if (!qpb.scope({{translate(cs, sel, qeb, qsm, s->challenges, memo), ProgramBuilder::FOLD, yr_idx}})) { set_error("gate: %s", qpb.error.c_str()); return ZKB_ERR_ARG; }
+            gi += run;
         }
         auto lactive = [&]() { return qeb.sub(qeb.sub(qeb.constant(one), qeb.col(q_llast, 0)), qeb.col(q_lblind, 0)); };
         if (pk->nsets) {
