@@ -120,9 +120,14 @@ def run_pass(plan, ps, src, dst, omega, threads, coset_in=None, in_scale=None, s
             for tid in range(threads):
                 for u in range(NG):
                     G = (tid + u * threads) & (total_groups - 1)
-                    c, gg = G >> lgpc, G & ((1 << lgpc) - 1)
-                    ploc = gg & (q - 1)
-                    rbase = ((gg >> lq) << (lq + R)) + ploc
+                    if first or log_c < 3:
+                        c, gg = G >> lgpc, G & ((1 << lgpc) - 1)
+                        ploc, ghi = gg & (q - 1), gg >> lq
+                    else:
+                        c = G & ((1 << log_c) - 1)
+                        rest, lgh = G >> log_c, lgpc - lq
+                        ghi, ploc = rest & ((1 << lgh) - 1), rest >> lgh
+                    rbase = (ghi << (lq + R)) + ploc
                     x = []
                     for m in range(E):
                         r = rbase + (m << lq)

@@ -129,3 +129,27 @@ def test_g1_sum_host_matches_oracle(oracle):
         acc = j if acc is None else oracle.g1_add(acc, j)
     exp = oracle.g1_to_affine(acc)
     assert (aff == exp).all() and comp == oracle.g1_compress(exp)
+
+
+def _deal_case(rank, world):
+    """the dealing of the multi-GPU create_proof (prover.cu `Deal`, mirrored by parallel.Deal): contiguous blocks, one in-place
+    all-gather, padding rows never read"""
+    from zkb200 import parallel
+    ok = True
+    for count in (1, 2, 3, 7, 8, 16, 49, 128):
+        d = parallel.Deal(count, rank, world)
+        owners = [sum(1 for r in range(world) if parallel.Deal(count, r, world).mine(i)) for i in range(count)]
+        ok &= all(o == (1 if d.on else world) for o in owners)          # every unit has exactly one owner (or is computed everywhere)
+        ok &= d.padded() >= count and (not d.on or d.padded() - count < world)
+        slab = torch.full((d.padded(), 4), -1, dtype=torch.int64)
+        for i in range(count):
+            if d.mine(i):
+                slab[i] = torch.tensor([i, 10 * i, rank, 7])
+        d.gather(slab)
+        exp_rank = [(i // d.blk if d.on else rank) for i in range(count)]
+        ok &= all(slab[i].tolist() == [i, 10 * i, exp_rank[i], 7] for i in range(count))
+    return ok
+
+
+def test_block_dealing_all_gather_gloo():
+    assert all(run_world(_deal_case, 2))

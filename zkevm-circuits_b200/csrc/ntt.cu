@@ -181,9 +181,25 @@ __device__ __forceinline__ void ntt_round(uint8_t *dbuf, const PassArgs &p, cons
         // a tile shorter than 8 x 256 elements (single-pass transforms below 2^11) wraps: the surplus threads redo a valid
         // group and write identical values, which keeps the register arrays free of divergent definitions
         const uint32_t G = (tid + u * NTT_THREADS) & (total_groups - 1);
-        const uint32_t c = G >> lgpc, g = G & ((1u << lgpc) - 1);
-        ploc[u] = g & (q - 1);
-        rbase[u] = ((g >> lq) << (lq + R)) + ploc[u];
+        uint32_t c, ghi;
+        if (FIRST || p.log_c < 3) {
+            // rows fastest: adjacent lanes read adjacent 32-byte elements of the TMA layout (and, with fewer than 8 columns per
+            // tile, the only mapping that keeps the 128-bit data accesses of a quarter-warp on 8 distinct bank groups)
+            c = G >> lgpc;
+            const uint32_t g = G & ((1u << lgpc) - 1);
+            ploc[u] = g & (q - 1);
+            ghi = g >> lq;
+        } else {
+            // columns fastest, then the block index, then the position inside the block: the lanes of a warp share ONE twiddle
+            // (position), which the shared-memory load broadcasts -- with rows fastest the twiddle loads of the middle rounds are
+            // strided by 2^(s+t) elements and replay up to 32 times (measured: 39 M of 80 M wavefronts per pass were replays);
+            // the data stays conflict free because the column stride A + 1 is odd
+            c = G & ((1u << p.log_c) - 1);
+            const uint32_t rest = G >> p.log_c, lgh = lgpc - lq;
+            ghi = rest & ((1u << lgh) - 1);
+            ploc[u] = rest >> lgh;
+        }
+        rbase[u] = (ghi << (lq + R)) + ploc[u];
         cbase[u] = c;
 #pragma unroll
         for (int m = 0; m < E; ++m) {

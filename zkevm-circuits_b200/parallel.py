@@ -32,6 +32,33 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class Deal:
+    """Host mirror of prover.cu's `Deal`: `count` independent units (columns, lookup arguments, coset parts) are cut into `world`
+    contiguous blocks of blk = ceil(count / world); rank r computes block r.  Results live in a slab of world * blk unit slots (the
+    tail is padding) so that ONE in-place all-gather -- every rank contributes its own block -- completes the slab on every rank."""
+
+    def __init__(self, count, rank, world):
+        self.count, self.rank, self.world = count, rank, world
+        self.on = world > 1 and count >= 2
+        self.blk = (count + world - 1) // world if self.on else count
+
+    def mine(self, i):
+        return (not self.on) or i // self.blk == self.rank
+
+    def padded(self):
+        return self.world * self.blk if self.on else self.count
+
+    def gather(self, slab, group=None):
+        """slab: tensor with padded() rows; this rank's block is filled; after the call every row < count is filled on every rank"""
+        import torch
+        import torch.distributed as dist
+        if not self.on:
+            return slab
+        parts = [slab[r * self.blk:(r + 1) * self.blk] for r in range(self.world)]   # views into the slab: an in-place all-gather
+        dist.all_gather(parts, slab[self.rank * self.blk:(self.rank + 1) * self.blk].clone(), group=group)
+        return slab
+
+
 def g1_sum_affine(points):
     """points: numpy uint64 (m, 8) -> (affine uint64[8], compressed bytes); host-only C-ABI call."""
     pts = np.ascontiguousarray(points, dtype=np.uint64)
