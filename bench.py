@@ -106,16 +106,15 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def load_oracle():
-    """the CPU oracle with an EXPLICIT OpenMP thread count (torchrun exports OMP_NUM_THREADS=1 to its workers) and threads spread over
-    the sockets, so that the CPU arm does not depend on the launcher or on first-touch luck"""
-    os.environ["OMP_NUM_THREADS"] = str(host_threads())
-    os.environ.setdefault("OMP_PROC_BIND", "spread")
-    os.environ.setdefault("OMP_PLACES", "cores")
+def load_oracle(threads=None):
+    """the CPU oracle with an EXPLICIT OpenMP thread count (torchrun exports OMP_NUM_THREADS=1 to its workers), so that the CPU arm does
+    not depend on the launcher"""
+    threads = threads or host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_lib
     orc = oracle_lib.load()
-    orc.set_num_threads(host_threads())     # the OpenMP runtime may already have been initialised with the launcher's value
+    orc.set_num_threads(threads)     # the OpenMP runtime may already have been initialised with the launcher's value
     return orc
 
 
@@ -155,28 +154,50 @@ def oracle_proof_seconds(k, advice, reps=1):
     return times, sc.shape
 
 
+PROOF_CPU_THREADS = 32   # the oracle prover's small-array stages get SLOWER with more threads (fork/join + spinning on boxes whose
+                         # cgroup grants fewer CPUs than sched_getaffinity reports: 25 s at 64 threads, 380-660 s at 128 on this pool)
+
+
+def _cpu_proof_child(k, steps):
+    """runs in a fresh interpreter (no CUDA context, no inherited OpenMP pool): prints one JSON line"""
+    orc = load_oracle(min(host_threads(), PROOF_CPU_THREADS))
+    times, shape = oracle_proof_seconds(k, ADVICE, reps=steps)
+    print(json.dumps({"k": k, "times": times, "cores": orc.num_threads()}), flush=True)
+
+
 def cpu_proof_sample(budget_s, steps):
-    """largest k <= 15 whose `steps` oracle proofs fit the budget (calibrated on k = 11); -> (k_sample, [seconds per proof])"""
-    t11, _ = oracle_proof_seconds(11, ADVICE, reps=1)
+    """oracle create_proof on a bounded sample of the same shape, in a SUBPROCESS with a hard timeout: calibrate on k = 11, then the
+    largest k <= 15 whose `steps` proofs fit the budget; -> (k_sample, [seconds per proof], threads)"""
+    env = dict(os.environ, OMP_NUM_THREADS=str(min(host_threads(), PROOF_CPU_THREADS)), OMP_WAIT_POLICY="passive", CUDA_VISIBLE_DEVICES="")
+
+    def child(k, reps, timeout):
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-proof-child", str(k), str(reps)], env=env, capture_output=True, text=True,
+                             timeout=timeout)
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if not lines:
+            raise RuntimeError("cpu proof child failed: " + out.stderr[-400:])
+        return json.loads(lines[-1])
+    r = child(11, 1, max(60.0, 4 * budget_s))
+    t11 = r["times"][0]
     k_s = 11
-    while k_s < 15 and t11[0] * (1 << (k_s + 1 - 11)) * steps <= budget_s:
+    while k_s < 15 and t11 * (1 << (k_s + 1 - 11)) * steps <= budget_s:
         k_s += 1
-    if k_s == 11:
-        return 11, t11
-    times, _ = oracle_proof_seconds(k_s, ADVICE, reps=steps)
-    return k_s, times
+    if k_s > 11:
+        try:
+            r = child(k_s, steps, max(120.0, 3 * budget_s))
+        except subprocess.TimeoutExpired:
+            k_s = 11
+    return k_s, r["times"], r["cores"]
 
 
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    orc = load_oracle()
     steps = max(1, min(args.steps, 3))
-    k_s, times = cpu_proof_sample(150.0, steps)
+    k_s, times, cores = cpu_proof_sample(150.0, steps)
     scale = 1 << (K_PROOF - k_s)
     sec = sorted(times)[len(times) // 2] * scale
-    cores = orc.num_threads()
     cfg = config_dict(args.gpus)
     cfg["reference_steps_cap"] = f"{len(times)} timed oracle proofs (cap 3; no warm-up needed on the CPU), asked for --steps {args.steps} --warmup {args.warmup}"
     line = {"impl": "reference", "metric": METRIC, "value": sec, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": 0,
@@ -302,7 +323,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--cpu-proof-child", nargs=2, type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_proof_child:
+        return _cpu_proof_child(*args.cpu_proof_child)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -456,10 +480,9 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            orc = load_oracle()
-            k_s, times = cpu_proof_sample(25.0, 1)
+            k_s, times, cores = cpu_proof_sample(25.0, 1)
             scale = 1 << (K_PROOF - k_s)
-            cpu_baseline = {"value": times[0] * scale, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            cpu_baseline = {"value": times[0] * scale, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"one oracle create_proof (restated halo2 prover over the OpenMP C oracle) of the same shape at k={k_s}: {times[0]:.2f} s, "
                                       f"scaled x{scale} (linear in rows: an underestimate of the CPU time)"}
         except Exception as e:

@@ -20,6 +20,9 @@
 #include <math.h>
 #ifdef _OPENMP
 #include <omp.h>
+/* loops shorter than this run on the calling thread: a fork/join over 128 threads costs more than 8 k field operations (the
+ * upstream prover's rayon `parallelize` makes the same kind of size-based decision) */
+#define ZKO_PAR_MIN 16384
 #endif
 #include "zko_field.h"
 #include "zko_curve.h"
@@ -47,7 +50,7 @@ static const zko_field_params *pick(int which) { return which ? &ZKO_FQ : &ZKO_F
 
 API void zko_field_binop(int which, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n) {
     const zko_field_params *F = pick(which);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= ZKO_PAR_MIN)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         const fe_t *x = (const fe_t *)(a + 4 * i), *y = (const fe_t *)(b + 4 * i);
         fe_t *o = (fe_t *)(out + 4 * i);
@@ -61,7 +64,7 @@ API void zko_field_binop(int which, int op, const uint64_t *a, const uint64_t *b
 }
 API void zko_field_unop(int which, int op, const uint64_t *a, uint64_t *out, uint64_t n) {
     const zko_field_params *F = pick(which);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= ZKO_PAR_MIN)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         const fe_t *x = (const fe_t *)(a + 4 * i);
         fe_t *o = (fe_t *)(out + 4 * i);
@@ -106,7 +109,7 @@ API void zko_best_fft(uint64_t *data, const uint64_t omega[4], uint32_t log_n) {
     fe_t *a = (fe_t *)data;
     const uint64_t n = 1ULL << log_n;
     if (log_n == 0) return;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= ZKO_PAR_MIN)
     for (int64_t k = 0; k < (int64_t)n; ++k) {
         uint64_t rk = bitrev((uint64_t)k, log_n);
         if ((uint64_t)k < rk) { fe_t t = a[k]; a[k] = a[rk]; a[rk] = t; }
@@ -120,7 +123,7 @@ API void zko_best_fft(uint64_t *data, const uint64_t omega[4], uint32_t log_n) {
         int nt = zko_num_threads();
         uint64_t blk = (half + nt - 1) / nt;
         if (blk == 0) blk = 1;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= ZKO_PAR_MIN)
         for (int64_t b = 0; b < (int64_t)((half + blk - 1) / blk); ++b) {
             uint64_t s = (uint64_t)b * blk, e = s + blk > half ? half : s + blk;
             uint64_t ex[4] = {s, 0, 0, 0};
@@ -136,7 +139,7 @@ API void zko_best_fft(uint64_t *data, const uint64_t omega[4], uint32_t log_n) {
     if (n >> local < (uint64_t)zko_num_threads()) local = 0;   /* too few blocks to keep all threads busy */
     if (local) {
         const uint64_t bsz = 1ULL << local;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= ZKO_PAR_MIN)
         for (int64_t b = 0; b < (int64_t)(n >> local); ++b) {
             fe_t *blk = a + (uint64_t)b * bsz;
             uint64_t chunk = 2, twiddle_chunk = half;
@@ -159,7 +162,7 @@ API void zko_best_fft(uint64_t *data, const uint64_t omega[4], uint32_t log_n) {
     uint64_t chunk = 2ULL << local, twiddle_chunk = half >> local;
     for (uint32_t layer = local; layer < log_n; ++layer) {
         const uint64_t hc = chunk / 2;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= ZKO_PAR_MIN)
         for (int64_t idx = 0; idx < (int64_t)half; ++idx) {
             uint64_t blk = (uint64_t)idx / hc, i = (uint64_t)idx % hc;
             fe_t *lo = &a[blk * chunk + i], *hi = lo + hc;

@@ -27,6 +27,7 @@
 //   per-element input scale are fused into the first / last register round.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
 
@@ -481,13 +482,19 @@ static int32_t get_plan(zkb_ctx *ctx, uint32_t log_n, const Fr &omega, NttPlan *
     // factor sizes: the final pass may be as long as a tile (2^11), the others are bounded by the shared-memory budget of two
     // resident CTAs (2^9); more, shorter passes cost no extra multiplies (every pass drops its A - 1 unit twiddles, which pays
     // for the extra boundary multiply per element), only one more trip through HBM
-    if (log_n <= NTT_MAX_BITS) { plan.npass = 1; plan.bits[0] = log_n; }
-    else if (log_n <= NTT_PREF_INNER_BITS + NTT_MAX_BITS) {
+    // ZKB_NTT_MAX_A (experiments): upper bound on every factor, e.g. 8 turns 2^20 into 7 + 7 + 6 (C >= 8 columns per tile in every pass)
+    int max_final = NTT_MAX_BITS, pref_inner = NTT_PREF_INNER_BITS;
+    if (const char *e = getenv("ZKB_NTT_MAX_A")) {
+        const int v = atoi(e);
+        if (v >= 6 && v <= NTT_MAX_BITS && 3 * v >= (int)log_n) { max_final = v; pref_inner = std::min(pref_inner, v); }
+    }
+    if ((int)log_n <= max_final) { plan.npass = 1; plan.bits[0] = log_n; }
+    else if ((int)log_n <= pref_inner + max_final) {
         plan.npass = 2;
-        plan.bits[0] = std::min<int>(NTT_PREF_INNER_BITS, (log_n + 1) / 2);
+        plan.bits[0] = std::min<int>(pref_inner, (log_n + 1) / 2);
         plan.bits[1] = log_n - plan.bits[0];
     } else {
-        const int cap = log_n > 2 * NTT_PREF_INNER_BITS + NTT_MAX_BITS ? NTT_MAX_INNER_BITS : NTT_PREF_INNER_BITS;
+        const int cap = (int)log_n > 2 * pref_inner + max_final ? NTT_MAX_INNER_BITS : pref_inner;
         plan.npass = 3;
         plan.bits[0] = std::min<int>(cap, (log_n + 2) / 3);
         plan.bits[1] = std::min<int>(cap, (log_n - plan.bits[0] + 1) / 2);
