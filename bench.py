@@ -154,6 +154,41 @@ def oracle_proof_seconds(k, advice, reps=1):
     return times, sc.shape
 
 
+def cpu_primitive_model(shape):
+    """Lower bound of a CPU create_proof from MEASURED oracle primitives (all host threads): one best_multiexp and one best_fft of the
+    circuit's size, multiplied by the number of commitments / transforms halo2's create_proof performs for this shape.
+    Quotient evaluation, scans, lookups' hash maps and witness generation are NOT included."""
+    import numpy as np
+    orc = load_oracle()
+    k, A, L, P = shape["k"], shape["advice_columns"], shape["lookup_arguments"], shape["permutation_columns"]
+    nf, ni, d = shape["fixed_columns"], shape["instance_columns"], shape["cs_degree"]
+    n = 1 << k
+    nsets = (P + (d - 2) - 1) // (d - 2)
+    rng = np.random.default_rng(5)
+
+    def rand_fr(m):
+        a = rng.integers(0, 1 << 64, size=(m, 4), dtype=np.uint64)
+        a[:, 3] = rng.integers(0, 0x30644E72E131A029, size=m, dtype=np.uint64)
+        return a
+    small = orc.g1_fixed_base_mul(orc.g1_generator(), rand_fr(1 << 12))
+    bases = np.tile(small, (n >> 12, 1)) if n >= (1 << 12) else small[:n]
+    s = rand_fr(n)
+    orc.best_multiexp(s[:1 << 10], bases[:1 << 10])
+    t0 = time.perf_counter(); orc.best_multiexp(s, bases); t_msm = time.perf_counter() - t0
+    w = orc.fr_omega(k)
+    a = rand_fr(n)
+    orc.best_fft(a, w, k)
+    t0 = time.perf_counter(); orc.best_fft(a, w, k); t_fft = time.perf_counter() - t0
+    ek = k + 3
+    t_ext = t_fft * ((1 << ek) * ek) / (n * k)
+    commits = A + 2 * L + nsets + 1 + (d - 1) + 2
+    iffts = A + 2 * L + nsets + ni
+    ext_ffts = A + nf + ni + P + nsets + 2 * L + 4 + 1
+    return {"seconds_lower_bound": commits * t_msm + iffts * t_fft + ext_ffts * t_ext, "msm_seconds": t_msm, "fft_seconds": t_fft,
+            "extended_fft_seconds_scaled": t_ext, "commitments": commits, "iffts": iffts, "extended_ffts": ext_ffts, "cores": orc.num_threads(),
+            "note": "measured oracle MSM / FFT x halo2's operation counts; excludes quotient evaluation, scans, lookups and witness generation"}
+
+
 PROOF_CPU_THREADS = 32   # the oracle prover's small-array stages get SLOWER with more threads (fork/join + spinning on boxes whose
                          # cgroup grants fewer CPUs than sched_getaffinity reports: 25 s at 64 threads, 380-660 s at 128 on this pool)
 
@@ -207,6 +242,11 @@ def run_reference(args):
                              "sample": f"oracle create_proof (restated halo2 prover, OpenMP field/NTT/MSM kernels) of the same shape at k={k_s}: "
                                        f"median {sorted(times)[len(times) // 2]:.2f} s, scaled x{scale} (linear in rows; the n log n parts make this an underestimate)"},
             "e2e": {"value": sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:   # context: what the C/OpenMP primitives alone would cost at the full size (the Python-orchestrated prover above is far slower)
+        shape = {"k": K_PROOF, "advice_columns": ADVICE, "lookup_arguments": 16, "permutation_columns": 49, "fixed_columns": 11, "instance_columns": 1, "cs_degree": 9}
+        line["cpu_baseline"]["primitive_model"] = cpu_primitive_model(shape)
+    except Exception as e:
+        line["cpu_baseline"]["primitive_model_error"] = repr(e)
     print(json.dumps(line), flush=True)
 
 
@@ -485,6 +525,7 @@ def main():
             cpu_baseline = {"value": times[0] * scale, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"one oracle create_proof (restated halo2 prover over the OpenMP C oracle) of the same shape at k={k_s}: {times[0]:.2f} s, "
                                       f"scaled x{scale} (linear in rows: an underestimate of the CPU time)"}
+            cpu_baseline["primitive_model"] = cpu_primitive_model(shape)
         except Exception as e:
             cpu_baseline = {"error": repr(e)}
 

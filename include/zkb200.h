@@ -279,6 +279,10 @@ ZKB_API int32_t zkb_transcript_script_host(int32_t kind, const uint8_t *ops, uin
                                            uint64_t cap, uint64_t *proof_len, uint64_t *challenges);
 ZKB_API int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const uint64_t *const *advice_columns,
                                        uint64_t *challenges_out);
+/* Witness-side overlap (zkevm-circuits/src/super_circuit.rs:714-806 assigns sub-circuit after sub-circuit): hand a
+ * finished, blinded advice column over BEFORE its phase is submitted.  The H2D copy runs on the copy stream while the caller keeps
+ * synthesising; zkb_prove_advice_phase then accepts NULL for that column.  The buffer must stay valid until the phase call.       */
+ZKB_API int32_t zkb_prove_upload_advice(zkb_session *s, uint32_t column, const uint64_t *values);
 ZKB_API int32_t zkb_prove_finish(zkb_session *s, const uint64_t *z_blinds, const uint64_t *phi_blinds,
                                  const uint64_t *random_poly, uint8_t *proof_out, uint64_t proof_cap, uint64_t *proof_len);
 ZKB_API int32_t zkb_session_destroy(zkb_session *s);

@@ -222,6 +222,8 @@ def test_callers_transcript_through_callbacks_writes_the_same_proof():
         def write_scalar(self, l): self.ops += 1; self.t.write_scalar(F.ints(l[None])[0])
         def write_point(self, l): self.ops += 1; self.t.write_point(l)
         def squeeze_challenge(self): self.ops += 1; return F.arr([self.t.squeeze()])[0]
+    # columns handed over one by one ahead of their phase (zkb_prove_upload_advice): same proof
+    assert Z.create_proof(*args, upload_ahead=True) == proof_lib
     mine = Mine()
     out = Z.create_proof(*args, transcript=Z.CallbackTranscript(mine))
     assert out == b"" and bytes(mine.t.buf) == proof_lib and mine.ops > 20

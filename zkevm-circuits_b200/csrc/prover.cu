@@ -104,6 +104,11 @@ __global__ void mul_arrays_kernel(const Fr *__restrict__ a, const Fr *__restrict
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i < n) fp_store(out + i, fp_mul(fp_load(a + i), fp_load(b + i)));
 }
+// a[i] *= c
+__global__ void scale_const_kernel(Fr *__restrict__ a, Fr c, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) fp_store(a + i, fp_mul(fp_load(a + i), c));
+}
 // out[i] -= low[i] for i < k (subtract a low-degree polynomial given on the device)
 __global__ void sub_low_kernel(Fr *__restrict__ out, const Fr *__restrict__ low, uint32_t k) {
     uint32_t i = threadIdx.x;   // one block of 256 threads: a rotation set has at most 256 points
@@ -215,6 +220,8 @@ struct zkb_session {
     std::vector<uint8_t> proof;
     DevPool pool;
     std::vector<Fr *> inst_values, inst_polys, adv_values;
+    // columns handed over ahead of their phase (zkb_prove_upload_advice): staged device copies, consumed by zkb_prove_advice_phase
+    std::map<uint32_t, Fr *> early_cols;
     std::vector<Fr> challenges;
     uint32_t next_phase = 0;
     bool finished = false;
@@ -368,6 +375,24 @@ static int32_t deal_gather(zkb_ctx *ctx, const Deal &d, void *slab, size_t unit_
 // (Deal) and the 64-byte results are all-gathered.
 static int32_t commit_many(zkb_pk *pk, const std::vector<Fr *> &cols, const G1Affine *bases, uint64_t len, std::vector<G1Affine> &out, cudaStream_t st) {
     zkb_ctx *ctx = pk->ctx;
+    if (ctx->nranks > 1 && cols.size() == 1 && len >= (1u << 14)) {
+        // a single commitment (random polynomial, SHPLONK's h and the final quotient) cannot be dealt: shard it by point range instead
+        // (SURVEY 8e): every rank reduces len / P points, the 64-byte partial sums are all-gathered and added on the host
+        const uint64_t P = (uint64_t)ctx->nranks, lo = len * (uint64_t)ctx->rank / P, hi = len * ((uint64_t)ctx->rank + 1) / P;
+        G1Affine part;
+        ZKB_TRY(msm_g1_device(ctx, cols[0] + lo, bases + lo, hi - lo, &part, st));
+        G1Affine *d_buf = nullptr;
+        ZKB_TRY(scratch_get(ctx, SCR_COMM, 16 * sizeof(G1Affine), (void **)&d_buf));
+        ZKB_CUDA(cudaMemcpyAsync(d_buf + ctx->rank, &part, sizeof(G1Affine), cudaMemcpyHostToDevice, st));
+        ZKB_TRY(comm_allgather(ctx, d_buf + ctx->rank, d_buf, sizeof(G1Affine), st));
+        G1Affine all[16];
+        ZKB_CUDA(cudaMemcpyAsync(all, d_buf, P * sizeof(G1Affine), cudaMemcpyDeviceToHost, st));
+        ZKB_CUDA(cudaStreamSynchronize(st));
+        G1Xyzz acc = G1Xyzz::identity();
+        for (uint64_t r = 0; r < P; ++r) g1_add_mixed(acc, all[r]);
+        out.assign(1, g1_to_affine(acc));
+        return ZKB_OK;
+    }
     const Deal d(ctx, cols.size());
     if (!d.on) return commit_many_local(pk, cols, bases, len, out, st);
     std::vector<Fr *> mine;
@@ -880,6 +905,20 @@ static int32_t prove_begin_common(zkb_pk *pk, int32_t transcript_kind, const zkb
     return ZKB_OK;
 }
 
+// Witness-side overlap: `synthesize` assigns sub-circuit after sub-circuit (super_circuit.rs:714-806), so the columns
+// of a phase become final one at a time.  The shim may hand each finished column over immediately: the copy runs on the copy stream
+// while Rust keeps synthesising, and zkb_prove_advice_phase later finds the column already in HBM (its pointer may then be NULL).
+extern "C" int32_t zkb_prove_upload_advice(zkb_session *s, uint32_t column, const uint64_t *values) {
+    ZKB_ARG(s && values && column < s->pk->cs.na);
+    zkb_pk *pk = s->pk;
+    if (s->finished || pk->cs.adv_phase[column] < s->next_phase) { set_error("column %u belongs to a phase that is already committed", column); return ZKB_ERR_STATE; }
+    ZKB_CUDA(cudaSetDevice(pk->ctx->device));
+    Fr *&d = s->early_cols[column];
+    if (!d) ZKB_TRY(s->pool.fr(pk->n, &d));
+    ZKB_CUDA(cudaMemcpyAsync(d, values, pk->n * sizeof(Fr), cudaMemcpyDefault, pk->ctx->copy_stream));
+    return ZKB_OK;
+}
+
 extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const uint64_t *const *advice_columns, uint64_t *challenges_out) {
     ZKB_ARG(s && advice_columns);
     zkb_pk *pk = s->pk;
@@ -895,8 +934,10 @@ extern "C" int32_t zkb_prove_advice_phase(zkb_session *s, uint32_t phase, const 
     std::vector<uint32_t> phase_idx;
     for (uint32_t c = 0; c < cs.na; ++c) {
         if (cs.adv_phase[c] != phase) continue;
-        ZKB_ARG(advice_columns[c] != nullptr);
-        phase_src.push_back(advice_columns[c]);
+        auto early = s->early_cols.find(c);
+        const uint64_t *src = advice_columns[c] ? advice_columns[c] : (early != s->early_cols.end() ? (const uint64_t *)early->second : nullptr);
+        if (!src) { set_error("advice column %u of phase %u was neither passed nor uploaded ahead", c, phase); return ZKB_ERR_ARG; }
+        phase_src.push_back(src);   // a staged copy is a device pointer: the gather into the phase slab below is then device-to-device
         phase_idx.push_back(c);
     }
     const size_t ncols = phase_src.size();
@@ -1101,23 +1142,32 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
     };
     std::vector<Fr *> zs(pk->nsets);
     {
-        Fr last_z = one;
-        Fr delta_pow = one;
         Fr delta;
         {   // DELTA = 7^(2^28)
             Fr seven = fr_from_u64(7);
             delta = seven;
             for (int i = 0; i < 28; ++i) delta = fp_sqr(delta);
         }
+        // Multi-GPU: the sets are dealt.  Upstream chains them (z_i[0] = last value of z_{i-1}), which is sequential; here every set is
+        // scanned from 1 and rescaled afterwards by c_i = product of the previous sets' last values -- the same field elements
+        // (z_i = c_i * z'_i row by row), with only the nsets last values crossing the ranks before the columns are gathered.
+        const Deal dp_sets(ctx, pk->nsets);
+        Fr *z_slab = nullptr;
+        ZKB_TRY(pool.fr(std::max<size_t>(1, dp_sets.padded()) * n, &z_slab));
+        for (uint32_t si = 0; si < pk->nsets; ++si) zs[si] = z_slab + (size_t)si * n;
         Fr *num, *den, *tmp;
         ZKB_TRY(pool.fr(n, &num));
         ZKB_TRY(pool.fr(n, &den));
         ZKB_TRY(pool.fr(n, &tmp));
+        std::vector<Fr> lasts(std::max<size_t>(1, dp_sets.padded()), one);
+        Fr last_z = one;
         for (uint32_t si = 0; si < pk->nsets; ++si) {
+            if (!dp_sets.mine(si)) continue;
             ExprBuilder eb;
             ProgramBuilder pb(eb);
             uint32_t nnum = 0, nden = 0;
             bool first = true;
+            Fr delta_pow = fp_pow_u64(delta, (uint64_t)si * pk->chunk);
             for (uint32_t j = si * pk->chunk; j < std::min<size_t>((si + 1) * pk->chunk, cs.perm.size()); ++j) {
                 const uint32_t v = eb.col(perm_slot_values(cs.perm[j]), 0);
                 const uint32_t dterm = eb.add(eb.add(v, eb.mul(eb.col(v_sigma0 + j, 0), eb.constant(beta))), eb.constant(gamma));
@@ -1137,11 +1187,29 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
             ZKB_TRY(batch_invert_device(ctx, den, tmp, n, st));
             mul_arrays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, tmp, den, n);  // den <- modified values
             ctx->launches++;
-            ZKB_TRY(pool.fr(n, &zs[si]));
-            ZKB_TRY(prefix_product_device(ctx, den, n, last_z, zs[si], st));
-            ZKB_CUDA(cudaMemcpyAsync(zs[si] + (n - bf), z_blinds + 4ull * bf * si, (size_t)bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            // one GPU: chained exactly like upstream (init = previous last value); dealt: from 1, rescaled below
+            ZKB_TRY(prefix_product_device(ctx, den, n, dp_sets.on ? one : last_z, zs[si], st));
             ZKB_CUDA(cudaMemcpyAsync(&last_z, zs[si] + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, st));
             ZKB_CUDA(cudaStreamSynchronize(st));
+            lasts[si] = last_z;
+            if (!dp_sets.on) ZKB_CUDA(cudaMemcpyAsync(zs[si] + (n - bf), z_blinds + 4ull * bf * si, (size_t)bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        }
+        if (dp_sets.on) {
+            Fr *d_l = nullptr;
+            ZKB_TRY(scratch_get(ctx, SCR_COMM, dp_sets.padded() * sizeof(Fr), (void **)&d_l));
+            ZKB_CUDA(cudaMemcpyAsync(d_l, lasts.data(), dp_sets.padded() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            ZKB_TRY(deal_gather(ctx, dp_sets, d_l, sizeof(Fr), st));
+            ZKB_CUDA(cudaMemcpyAsync(lasts.data(), d_l, dp_sets.padded() * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            ZKB_CUDA(cudaStreamSynchronize(st));
+            Fr c = one;   // c_i = prod_{j < i} last'_j
+            for (uint32_t si = 0; si < pk->nsets; ++si) {
+                if (dp_sets.mine(si)) {
+                    if (!(c == one)) { scale_const_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zs[si], c, n); ctx->launches++; }
+                    ZKB_CUDA(cudaMemcpyAsync(zs[si] + (n - bf), z_blinds + 4ull * bf * si, (size_t)bf * sizeof(Fr), cudaMemcpyHostToDevice, st));
+                }
+                c = fp_mul(c, lasts[si]);
+            }
+            ZKB_TRY(deal_gather(ctx, dp_sets, z_slab, n * sizeof(Fr), st));
         }
     }
     {
@@ -1519,8 +1587,21 @@ static int32_t prove_finish_impl(zkb_session *s, const uint64_t *z_blinds, const
         for (size_t i : kv.second) ptrs.push_back(const_cast<Fr *>(reqs[i].poly));
         Fr **d_p = nullptr;
         ZKB_TRY(upload_table(pool, ptrs, &d_p, st));
-        std::vector<Fr> res(ptrs.size());
-        ZKB_TRY(poly_eval_device(ctx, d_p, (uint32_t)ptrs.size(), n, pt, res.data(), st));
+        // multi-GPU: the polynomials of a rotation are dealt, the 32-byte results all-gathered
+        const Deal de(ctx, ptrs.size());
+        std::vector<Fr> res(std::max<size_t>(1, de.padded()));
+        if (!de.on) {
+            ZKB_TRY(poly_eval_device(ctx, d_p, (uint32_t)ptrs.size(), n, pt, res.data(), st));
+        } else {
+            const size_t lo = (size_t)de.rank * de.blk, hi = std::min(ptrs.size(), lo + de.blk);
+            if (hi > lo) ZKB_TRY(poly_eval_device(ctx, d_p + lo, (uint32_t)(hi - lo), n, pt, res.data() + lo, st));
+            Fr *d_r = nullptr;
+            ZKB_TRY(scratch_get(ctx, SCR_COMM, de.padded() * sizeof(Fr), (void **)&d_r));
+            ZKB_CUDA(cudaMemcpyAsync(d_r + lo, res.data() + lo, de.blk * sizeof(Fr), cudaMemcpyHostToDevice, st));
+            ZKB_TRY(deal_gather(ctx, de, d_r, sizeof(Fr), st));
+            ZKB_CUDA(cudaMemcpyAsync(res.data(), d_r, de.padded() * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+            ZKB_CUDA(cudaStreamSynchronize(st));
+        }
         for (size_t t = 0; t < kv.second.size(); ++t) evals[kv.second[t]] = res[t];
     }
     for (size_t i = 0; i < n_written; ++i) tr_write_scalar(s, evals[i]);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "zkb_keccak256_host": (ctypes.c_int32, [_vp, ctypes.c_uint64, _vp]),
     "zkb_transcript_script_host": (ctypes.c_int32, [ctypes.c_int32, _vp, ctypes.c_uint64, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
     "zkb_prove_advice_phase": (ctypes.c_int32, [_vp, ctypes.c_uint32, _vp, _vp]),
+    "zkb_prove_upload_advice": (ctypes.c_int32, [_vp, ctypes.c_uint32, _vp]),
     "zkb_prove_finish": (ctypes.c_int32, [_vp, _vp, _vp, _vp, _vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
     "zkb_session_destroy": (ctypes.c_int32, [_vp]),
 }

@@ -226,7 +226,7 @@ class CallbackTranscript:
         self.vt = _TranscriptVtable(None, *self._keep)
 
 
-def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blinds, random_poly, transcript="blake2b"):
+def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blinds, random_poly, transcript="blake2b", upload_ahead=False):
     """Mirror of plonk::create_proof for one circuit; transcript = "blake2b" (Blake2bWrite, the reference's benches) or "poseidon"
     (snark-verifier-sdk's PoseidonTranscript, what gen_snark_shplonk uses) or "evm" (snark-verifier's EvmTranscript over Keccak-256,
     what gen_evm_proof_shplonk uses; proof items uncompressed big-endian) or a CallbackTranscript around the caller's own transcript
@@ -257,6 +257,12 @@ def create_proof(pk, transcript_repr, instances, synthesize, z_blinds, phi_blind
             for c, a in enumerate(arrs):
                 if cs.advice_phase[c] == phase:
                     assert a is not None and a.shape == (cs.n, 4) and a.dtype == np.uint64
+            if upload_ahead:   # column by column ahead of the phase call (zkb_prove_upload_advice), then NULL pointers in the phase call
+                idx = [c for c, a in enumerate(arrs) if a is not None]
+                keep_up, utbl = _ptr_array([arrs[c] for c in idx])      # keep_up holds the (contiguous) buffers alive until the phase call returns
+                for t, c in enumerate(idx):
+                    check(lib.zkb_prove_upload_advice(sess, c, _vp(utbl[t])))
+                arrs = [None] * len(arrs)
             ka, atbl = _ptr_array(arrs)
             check(lib.zkb_prove_advice_phase(sess, phase, ctypes.cast(atbl, _vp), _vp(ch_buf.ctypes.data)))
             for i, ph in enumerate(cs.challenge_phase):
