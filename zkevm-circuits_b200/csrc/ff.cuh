@@ -32,6 +32,10 @@ struct FrParams {
         constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
         return v[i];
     }
+    FF_HD static constexpr uint32_t P2(int i) {  // 2p (lazy-reduction bound of the NTT butterflies)
+        constexpr uint32_t v[8] = {0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u, 0x0302b0bau, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
+        return v[i];
+    }
     FF_HD static constexpr uint32_t R1(int i) {  // R mod p
         constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
         return v[i];
@@ -46,6 +50,10 @@ struct FqParams {
     static constexpr uint32_t INV = 0xe4866389u;
     FF_HD static constexpr uint32_t P(int i) {
         constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    FF_HD static constexpr uint32_t P2(int i) {  // 2p
+        constexpr uint32_t v[8] = {0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
         return v[i];
     }
     FF_HD static constexpr uint32_t R1(int i) {
@@ -239,8 +247,11 @@ FF_D void chain_stray_mad_nc(uint32_t &x0, uint32_t stray, uint32_t &c0, uint32_
 }  // namespace detail
 #endif
 
-template <class PR>
-FF_HD Fp<PR> fp_mul(const Fp<PR> &a, const Fp<PR> &b) {
+// REDUCE = false: the final conditional subtraction is skipped and the result is only guaranteed < 2p ("lazy" form, used by the NTT
+// butterflies).  Bounds (word-serial CIOS): the running value stays < a + p and the result is < a*b/R + p, so with R = 2^256 > 4p the
+// lazy product of a < 4p (first operand, the one that feeds the multiply chains) and b < p is < 2p and nothing overflows 8 limbs.
+template <class PR, bool REDUCE>
+FF_HD Fp<PR> fp_mul_t(const Fp<PR> &a, const Fp<PR> &b) {
     Fp<PR> r;
 #if defined(__CUDA_ARCH__)
     using namespace detail;
@@ -278,6 +289,7 @@ FF_HD Fp<PR> fp_mul(const Fp<PR> &a, const Fp<PR> &b) {
         : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
         : "r"(x1), "r"(x2), "r"(x3), "r"(x4), "r"(x5), "r"(x6), "r"(x7), "r"(x8),
           "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(y4), "r"(y5), "r"(y6), "r"(y7));
+    if (!REDUCE) return r;
     Fp<PR> t;
     uint32_t borrow;
     asm("sub.cc.u32 %0, %9, %17;\n\t"
@@ -329,9 +341,100 @@ FF_HD Fp<PR> fp_mul(const Fp<PR> &a, const Fp<PR> &b) {
 }
 
 template <class PR>
+FF_HD Fp<PR> fp_mul(const Fp<PR> &a, const Fp<PR> &b) { return fp_mul_t<PR, true>(a, b); }
+// a < 4p, b < p (or both < 2p)  ->  a*b/R mod p as a representative < 2p
+template <class PR>
+FF_HD Fp<PR> fp_mul_lazy(const Fp<PR> &a, const Fp<PR> &b) { return fp_mul_t<PR, false>(a, b); }
+
+template <class PR>
 FF_HD Fp<PR> fp_sqr(const Fp<PR> &a) {
     return fp_mul(a, a);
 }
+
+#if defined(__CUDACC__)
+// ---- lazy (< 2p) arithmetic for the NTT butterflies (device only) --------------------------------------------------------
+// a, b < 2p  ->  a + b reduced into [0, 2p)
+template <class PR>
+__device__ __forceinline__ Fp<PR> fp_add_lazy(const Fp<PR> &a, const Fp<PR> &b) {
+    Fp<PR> r, t;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]), "=r"(t.l[7]), "=r"(borrow)
+        : "r"(r.l[0]), "r"(r.l[1]), "r"(r.l[2]), "r"(r.l[3]), "r"(r.l[4]), "r"(r.l[5]), "r"(r.l[6]), "r"(r.l[7]),
+          "r"(PR::P2(0)), "r"(PR::P2(1)), "r"(PR::P2(2)), "r"(PR::P2(3)), "r"(PR::P2(4)), "r"(PR::P2(5)), "r"(PR::P2(6)), "r"(PR::P2(7)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = borrow ? r.l[i] : t.l[i];
+    return r;
+}
+// a, b < 2p  ->  a - b + 2p  in (0, 4p): no conditional (the wrap of a - b modulo 2^256 is undone by the addition)
+template <class PR>
+__device__ __forceinline__ Fp<PR> fp_sub_lazy(const Fp<PR> &a, const Fp<PR> &b) {
+    Fp<PR> r;
+    asm("sub.cc.u32 %0, %8, %16;\n\t"
+        "subc.cc.u32 %1, %9, %17;\n\t"
+        "subc.cc.u32 %2, %10, %18;\n\t"
+        "subc.cc.u32 %3, %11, %19;\n\t"
+        "subc.cc.u32 %4, %12, %20;\n\t"
+        "subc.cc.u32 %5, %13, %21;\n\t"
+        "subc.cc.u32 %6, %14, %22;\n\t"
+        "subc.u32 %7, %15, %23;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(r.l[0]), "+r"(r.l[1]), "+r"(r.l[2]), "+r"(r.l[3]), "+r"(r.l[4]), "+r"(r.l[5]), "+r"(r.l[6]), "+r"(r.l[7])
+        : "r"(PR::P2(0)), "r"(PR::P2(1)), "r"(PR::P2(2)), "r"(PR::P2(3)), "r"(PR::P2(4)), "r"(PR::P2(5)), "r"(PR::P2(6)), "r"(PR::P2(7)));
+    return r;
+}
+// x < 4p -> [0, 2p)   /   x < 2p -> [0, p): one conditional subtraction of 2p (TWO = true) or p
+template <class PR, bool TWO>
+__device__ __forceinline__ Fp<PR> fp_cond_sub(const Fp<PR> &x) {
+    Fp<PR> t, r;
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]), "=r"(t.l[7]), "=r"(borrow)
+        : "r"(x.l[0]), "r"(x.l[1]), "r"(x.l[2]), "r"(x.l[3]), "r"(x.l[4]), "r"(x.l[5]), "r"(x.l[6]), "r"(x.l[7]),
+          "r"(TWO ? PR::P2(0) : PR::P(0)), "r"(TWO ? PR::P2(1) : PR::P(1)), "r"(TWO ? PR::P2(2) : PR::P(2)), "r"(TWO ? PR::P2(3) : PR::P(3)),
+          "r"(TWO ? PR::P2(4) : PR::P(4)), "r"(TWO ? PR::P2(5) : PR::P(5)), "r"(TWO ? PR::P2(6) : PR::P(6)), "r"(TWO ? PR::P2(7) : PR::P(7)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = borrow ? x.l[i] : t.l[i];
+    return r;
+}
+#endif
 
 // a^e, e given as 8 x u32 little-endian (plain integer)
 template <class PR>

@@ -219,9 +219,9 @@ __device__ __forceinline__ void ntt_round(uint8_t *dbuf, const PassArgs &p, cons
                     const uint32_t idx = (r << p.log_inner) + ti.c0 + cbase[u];   // first pass: outer == 0
                     if (p.coset_in) {
                         const uint32_t z = idx % 3;
-                        if (z) x[u * E + m] = fp_mul(x[u * E + m], zeta_pow(z));
+                        if (z) x[u * E + m] = fp_mul_lazy(x[u * E + m], zeta_pow(z));
                     }
-                    if (p.has_in_scale) x[u * E + m] = fp_mul(x[u * E + m], fp_load(p.in_scale + idx));
+                    if (p.has_in_scale) x[u * E + m] = fp_mul_lazy(x[u * E + m], fp_load(p.in_scale + idx));
                 }
             }
         }
@@ -236,15 +236,18 @@ __device__ __forceinline__ void ntt_round(uint8_t *dbuf, const PassArgs &p, cons
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 if ((m & d) == 0) {
+                    // lazy butterflies: every element stays a representative < 2p; u - v + 2p (< 4p, no conditional) feeds the
+                    // multiply chains directly and the product comes back < 2p without the final conditional subtraction
                     const Fr uu = x[u * E + m], vv = x[u * E + m + d];
-                    x[u * E + m] = fp_add(uu, vv);
-                    Fr dif = fp_sub(uu, vv);
+                    x[u * E + m] = fp_add_lazy(uu, vv);
+                    Fr dif = fp_sub_lazy(uu, vv);
                     if (LAST) {
-                        if ((m & (d - 1)) != 0) dif = fp_mul(dif, ld_lin(loc_sm, (uint32_t)(m & (d - 1)) << (s + t)));
+                        if ((m & (d - 1)) != 0) dif = fp_mul_lazy(dif, ld_lin(loc_sm, (uint32_t)(m & (d - 1)) << (s + t)));
+                        else dif = fp_cond_sub<FrParams, true>(dif);
                     } else if (!last_trivial) {
                         const uint32_t pos = ploc[u] + ((uint32_t)(m & (d - 1)) << lq);
-                        dif = fp_mul(dif, ld_lin(loc_sm, pos << (s + t)));
-                    }
+                        dif = fp_mul_lazy(dif, ld_lin(loc_sm, pos << (s + t)));
+                    } else dif = fp_cond_sub<FrParams, true>(dif);
                     x[u * E + m + d] = dif;
                 }
             }
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_CTAS_PER_SM) ntt_tile_kernel(
                 if (tid < chunk_elems) {
                     const uint32_t c = e & (C - 1), q = e >> p.log_c;
                     const uint32_t k = __brev(q) >> (32 - a);   // a >= 1 in non-final passes
-                    const Fr v = fp_mul(ld_l1(lo, hi, c * (A + 1) + swz(q)), ld_lin(twring + slot * (NTT_TW_SLOT_ELEMS * 32u), tid));
+                    const Fr v = fp_mul_lazy(ld_l1(lo, hi, c * (A + 1) + swz(q)), ld_lin(twring + slot * (NTT_TW_SLOT_ELEMS * 32u), tid));   // < 2p: the next pass takes it lazily
                     const uint64_t oidx = ((((uint64_t)ti.outer << a) + k) << p.log_inner) + ti.c0 + c;
                     fp_store_stream(out + oidx, v);
                 }
@@ -379,12 +382,13 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_CTAS_PER_SM) ntt_tile_kernel(
                     const uint32_t k = a ? (__brev(q) >> (32 - a)) : 0;
                     Fr v = ld_l1(lo, hi, c * (A + 1) + swz(q));
                     const uint64_t oidx = obase + c + ((uint64_t)k << (p.a1 + p.a2));
-                    if (p.use_scale) v = fp_mul(v, fp_load(p.scale));
+                    if (p.use_scale) v = fp_mul_lazy(v, fp_load(p.scale));
                     if (p.coset_out) {
                         const uint32_t m = (uint32_t)(oidx % 3);
-                        if (m) v = fp_mul(v, zeta_pow(3 - m));  // ZETA^(-m) = ZETA^(3-m)
+                        if (m) v = fp_mul_lazy(v, zeta_pow(3 - m));  // ZETA^(-m) = ZETA^(3-m)
                     }
-                    if (p.out_tw) v = fp_mul(v, fp_load(p.out_tw + oidx));   // sharded transform: omega^(rank * k2)
+                    if (p.out_tw) v = fp_mul_lazy(v, fp_load(p.out_tw + oidx));   // sharded transform: omega^(rank * k2)
+                    v = fp_cond_sub<FrParams, false>(v);   // leave the lazy domain: results are canonical (< p) like best_fft's
                     if (p.peer_routed) {   // ... and straight into the owner's window (peer store over NVLink)
                         Fr *w = p.peers[oidx >> p.peer_log_blk];
                         fp_store_stream(w + ((uint64_t)p.peer_rank << p.peer_log_blk) + (oidx & ((1ull << p.peer_log_blk) - 1)), v);
