@@ -16,4 +16,10 @@ if [ -n "$TRACE_VARIANTS" ]; then
   done
   grep -E "^==|seconds_traced|zkb trace" gpurun_out/${T}_variants.log | cut -c1-400
 fi
-ls -la gpurun_out | tail -8
+if [ -n "$LAUNCH_LIST" ]; then timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${T}_launches_bench.log 2>&1; wc -l gpurun_out/${T}_launches_bench.csv; fi
+if [ -n "$NCU_PROOF" ]; then
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:expr_kernel -s 55 -c 2 -o gpurun_out/${T}_expr -f python scripts/proof_trace.py super 20 128 > gpurun_out/${T}_ncu_expr.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:msm_acc_chunk -s 2 -c 1 -o gpurun_out/${T}_msmacc -f python scripts/proof_trace.py super 20 128 > gpurun_out/${T}_ncu_msmacc.log 2>&1
+fi
+if [ -n "$SMOKE" ]; then timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2; fi
+ls -la gpurun_out | tail -12
