@@ -11,6 +11,8 @@ def dram_per_launch(path):
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, ms = [], []
     for r in data:
+        if "nan" in (r[ir].lower(), r[iw].lower()) or "nan" in r[ir].lower() or "nan" in r[iw].lower():
+            continue     # a replay pass that lost its counters
         tot.append(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
         ms.append(float(r[it]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[it], 1.0))
     return {"dram_bytes_per_launch": sum(tot) / len(tot), "launches_captured": len(tot), "ms_per_launch_under_ncu": sum(ms) / len(ms)}
