@@ -431,6 +431,7 @@ def main():
     prof = {nm: ctx.prof_read(i) for i, nm in enumerate(names)}
     ctx.prof_enable(False)
     acct = proof_accounting(sc.shape, prof)
+    sc_shape_degree = sc.shape["cs_degree"]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -448,16 +449,27 @@ def main():
                        "achieved_gbs": per_launch_bytes / (ms / cnt * 1e-3) / 1e9}
     dom = max(kernels, key=lambda nm: kernels[nm]["ms_per_proof"])
     # dram bytes per launch of the dominant kernel from the committed ncu --set full capture of this command (profiles/), if present
-    traffic = None
+    traffic, traffic_note = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_proof_k20_traffic.json")))
-        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+        per = tj.get(dom, {}).get("dram_bytes_per_launch")
+        if per and dom == "expr_kernel":
+            # the ncu capture is one QUOTIENT launch (one coset part); the class also holds the small value-domain programs (lookup
+            # compression, permutation / grand-sum terms), so express it per average launch of the class like `achieved`
+            parts = 8 if sc_shape_degree == 9 else 4
+            traffic = parts * per / kernels[dom]["launches_per_proof"]
+            traffic_note = (f"{parts} quotient launches x {per / 1e9:.1f} GB (ncu --set full, profiles/r02_expr_kernel_k20_ncu.txt) / "
+                            f"{kernels[dom]['launches_per_proof']} launches of the class; algorithmic = {acct[dom]['alg_bytes'] / parts / 1e9:.1f} GB per quotient launch: the "
+                            "interpreter re-reads a column at every use and its local-memory register file competes for L2 (DESIGN.md 3.4)")
+        elif per:
+            traffic = per
+            traffic_note = "dram bytes of one launch (ncu --set full, profiles/)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["achieved_gbs"] / peak,
                 "peak_source": "MEASURED_PEAKS.json (sustained copy bandwidth: the kernel runs inside a long step)" if peaks else "fallback 6650 GB/s",
-                "traffic": traffic,
+                "traffic": traffic, "traffic_note": traffic_note,
                 "note": "dominant kernel of the proof by measured device time; all three hot kernels are bound by the integer-multiply pipe "
                         "(254-bit Montgomery arithmetic), not by HBM: see DESIGN.md section 2 and profiles/r02_microbench_pipes.txt",
                 "kernels": kernels}
