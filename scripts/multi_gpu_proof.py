@@ -3,7 +3,7 @@ Multi-GPU create_proof (commitment batches and quotient coset parts dealt across
 single-GPU proof; reports the wall-clock of both (max over ranks)."""
 import os, sys, json, time, hashlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch, torch.distributed as dist
 
 
@@ -12,7 +12,7 @@ def run(k, ng, nl, npm, reps=3):
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     import zkb200
     from zkb200 import plonk as Z
-    from zkb200.synth import WideCircuit
+    from wide_circuit import WideCircuit
     from zkb200.params import ParamsKZG
     wc = WideCircuit(k, n_gates=ng, n_lookups=nl, n_perm=npm, two_phase=True, seed=3)
     params = ParamsKZG.unsafe_setup_with_s(k, 1234)

@@ -2,14 +2,14 @@
 usage: python scripts/proof_bench.py K N_GATES N_LOOKUPS N_PERM [REPS]"""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 
 
 def run(k, n_gates, n_lookups, n_perm, reps=2, two_phase=True):
     import zkb200
     from zkb200 import plonk as Z
-    from zkb200.synth import WideCircuit
+    from wide_circuit import WideCircuit
     from zkb200.params import ParamsKZG
     ctx = zkb200.default_context()
     t0 = time.perf_counter()

@@ -46,7 +46,7 @@ def test_params_setup_matches_oracle(oracle):
                                   (9, dict(n_gates=4, n_lookups=1, n_perm=3, two_phase=False))])
 def test_wide_circuit_matches_oracle(k, kw):
     from zkb200 import plonk as Z
-    from zkb200.synth import WideCircuit
+    from wide_circuit import WideCircuit
     from zkb200.params import ParamsKZG
     wc = WideCircuit(k, seed=k, **kw)
     cs = to_oracle_cs(wc.cs)

@@ -1,4 +1,6 @@
-"""Synthetic, satisfiable, SuperCircuit-/Keccak-shaped constraint systems with vectorised witness generation.
+"""(test / benchmark infrastructure, not product code -- moved out of the package after the round-1 review)
+Synthetic, satisfiable, degree-9 constraint systems with vectorised witness generation (the small round-1 stand-in; the SURVEY-shaped
+ones are in tests/standins.py).
 
 The reference's circuits cannot be synthesised without Rust, so the benchmarks and large parity
 tests use stand-ins with the same prover-relevant shape: many advice columns, custom gates with rotations, degree-9
@@ -8,10 +10,10 @@ the product's own CUDA field kernels (in the real system they come from Rust `sy
 """
 import numpy as np
 
-from . import arithmetic as A
-from . import poly
-from .plonk import ConstraintSystem, Expression as E, ADVICE
-from .params import fr_scalar_dev, fr_ints_to_dev, bcast, fr_pow2k_dev
+from zkb200 import arithmetic as A
+from zkb200 import poly
+from zkb200.plonk import ConstraintSystem, Expression as E, ADVICE
+from zkb200.params import fr_scalar_dev, fr_ints_to_dev, bcast, fr_pow2k_dev
 
 
 class WideCircuit:
